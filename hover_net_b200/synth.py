@@ -1,0 +1,136 @@
+"""Seeded synthetic inputs: a well-conditioned HoVer-Net checkpoint, RGB patches, nuclei pred maps.
+
+No datasets or trained checkpoints are reachable (no network), and the reference's own
+`weights_init` (reference `models/hovernet/net_utils.py:18-32`) drives logits to ~1e4, where two
+fp32 runs of the reference graph disagree by several 1e-2.  The generator below
+draws every tensor from `numpy.random.default_rng(seed)` with variance-preserving scales and
+non-trivial BatchNorm statistics, so outputs are O(1) and a 1e-4 parity bar is meaningful, and so
+the same checkpoint can be rebuilt bit-identically anywhere from (mode, nr_types, seed).
+
+`synth_pred_map` follows the HV-map definition of reference `models/hovernet/targets.py:57-93`
+(per-instance x/y offsets from the rounded centre of mass, negatives scaled by -min, positives by
+max) to produce nuclei-like inputs for the post-processing path.
+"""
+import numpy as np
+
+from .arch import state_dict_spec
+
+_HEAD_GAIN = {"np": 0.5, "hv": 0.25, "tp": 0.5}
+
+
+def make_state_dict(mode="original", nr_types=None, seed=0):
+    """name -> np.ndarray (float32; int64 for num_batches_tracked), keys == reference state_dict."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for name, shape in state_dict_spec(mode, nr_types).items():
+        if name.endswith("num_batches_tracked"):
+            sd[name] = np.array(1, dtype=np.int64)
+        elif name == "upsample2x.unpool_mat":
+            sd[name] = np.ones((2, 2), dtype=np.float32)
+        elif name.endswith("running_var"):
+            sd[name] = rng.uniform(0.6, 1.6, shape).astype(np.float32)
+        elif name.endswith("running_mean"):
+            sd[name] = (0.2 * rng.standard_normal(shape)).astype(np.float32)
+        elif name.endswith(".bias") and len(shape) == 1 and ".u0.conv." not in name:
+            sd[name] = (0.2 * rng.standard_normal(shape)).astype(np.float32)  # BN beta
+        elif name.endswith(".weight") and len(shape) == 1:
+            sd[name] = rng.uniform(0.7, 1.3, shape).astype(np.float32)  # BN gamma
+        elif name.endswith(".u0.conv.bias"):
+            sd[name] = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+        else:  # conv weight OIHW
+            o, i, kh, kw = shape
+            fan_in = i * kh * kw
+            std = np.sqrt(2.0 / fan_in)
+            if name.endswith("conv3.weight"):
+                std *= 0.4  # damp the residual branch so the running sum stays O(1..10)
+            elif name.endswith("shortcut.weight") or name == "conv_bot.weight":
+                std = np.sqrt(1.0 / fan_in)
+            elif name == "conv0./.weight":
+                std = np.sqrt(6.0 / fan_in)  # input is 0..1 with mean ~0.5
+            elif ".u0.conv." in name:
+                branch = name.split(".")[1]
+                std = _HEAD_GAIN[branch] * np.sqrt(1.0 / fan_in)
+            elif "conv2.weight" in name and ".dense." in name:
+                std = np.sqrt(2.0 / fan_in)
+            sd[name] = (std * rng.standard_normal(shape)).astype(np.float32)
+    return sd
+
+
+def make_patches(batch, size, seed=0):
+    """uint8 [B,size,size,3]: smooth H&E-like blobs plus iid noise (seeded)."""
+    rng = np.random.default_rng(1000 + seed)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
+    out = np.empty((batch, size, size, 3), dtype=np.uint8)
+    for b in range(batch):
+        img = np.full((size, size, 3), 200.0, dtype=np.float32)
+        for _ in range(24):
+            cy, cx = rng.uniform(0, size, 2)
+            r = rng.uniform(5, 16)
+            w = np.exp(-(((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * r * r)))
+            col = rng.uniform(40, 160, 3).astype(np.float32)
+            img -= w[..., None] * (200.0 - col)
+        img += rng.normal(0, 12, img.shape)
+        out[b] = np.clip(img, 0, 255).astype(np.uint8)
+    return out
+
+
+def synth_instances(h, w, seed=0, density=1.0 / 900.0, rmin=6.0, rmax=14.0):
+    """int32 [h,w] instance map of random (possibly touching, never overlapping) ellipses."""
+    rng = np.random.default_rng(2000 + seed)
+    inst = np.zeros((h, w), dtype=np.int32)
+    n = max(1, int(round(h * w * density)))
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    nid = 0
+    for _ in range(n):
+        cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+        a, b = rng.uniform(rmin, rmax, 2)
+        th = rng.uniform(0, np.pi)
+        c, s = np.cos(th), np.sin(th)
+        u = (xx - cx) * c + (yy - cy) * s
+        v = -(xx - cx) * s + (yy - cy) * c
+        m = ((u / a) ** 2 + (v / b) ** 2) <= 1.0
+        m &= inst == 0
+        if m.sum() < 12:
+            continue
+        nid += 1
+        inst[m] = nid
+    return inst
+
+
+def synth_pred_map(h, w, nr_types=None, seed=0, **kw):
+    """float32 [h,w,C] pred map like `infer_step` output: [tp?, np_prob, hv_x, hv_y]."""
+    rng = np.random.default_rng(3000 + seed)
+    inst = synth_instances(h, w, seed=seed, **kw)
+    hx = np.zeros((h, w), dtype=np.float32)
+    hy = np.zeros((h, w), dtype=np.float32)
+    tp = np.zeros((h, w), dtype=np.float32)
+    for i in range(1, int(inst.max()) + 1):
+        ys, xs = np.nonzero(inst == i)
+        if ys.size == 0:
+            continue
+        cy = int(ys.mean() + 0.5)
+        cx = int(xs.mean() + 0.5)
+        dx = (xs - cx).astype(np.float32)
+        dy = (ys - cy).astype(np.float32)
+        if (dx < 0).any():
+            dx[dx < 0] /= -dx.min()
+        if (dx > 0).any():
+            dx[dx > 0] /= dx.max()
+        if (dy < 0).any():
+            dy[dy < 0] /= -dy.min()
+        if (dy > 0).any():
+            dy[dy > 0] /= dy.max()
+        hx[ys, xs] = dx
+        hy[ys, xs] = dy
+        if nr_types is not None:
+            tp[ys, xs] = rng.integers(1, nr_types)
+    fg = (inst > 0).astype(np.float32)
+    npm = np.clip(0.9 * fg + rng.normal(0, 0.03, (h, w)), 0, 1).astype(np.float32)
+    hx = (hx + rng.normal(0, 0.02, (h, w))).astype(np.float32)
+    hy = (hy + rng.normal(0, 0.02, (h, w))).astype(np.float32)
+    chans = [npm, hx, hy]
+    if nr_types is not None:
+        flip = rng.uniform(0, 1, (h, w)) < 0.05
+        tp = np.where(flip, rng.integers(0, nr_types, (h, w)).astype(np.float32), tp)
+        chans = [tp.astype(np.float32)] + chans
+    return np.stack(chans, axis=-1).astype(np.float32)
