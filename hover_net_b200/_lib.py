@@ -1,0 +1,207 @@
+"""ctypes binding of libhvn.so (include/hvn.h).  There is no CPU fallback: if the CUDA library is
+missing or no sm_100 device is present, every entry point raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhvn.so")
+ROW_LEN = 10
+_lib = None
+
+
+class HvnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libhvn error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HvnError(-2, "libhvn.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                               "this package has no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        L.hvn_last_error.restype = ctypes.c_char_p
+        L.hvn_get_counter.restype = ctypes.c_int64
+        L.hvn_get_counter.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.hvn_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
+        for name in ("hvn_malloc", "hvn_malloc_host"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        for name in ("hvn_memcpy_h2d", "hvn_memcpy_d2h"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        for name in ("hvn_free", "hvn_free_host"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise HvnError(rc, lib().hvn_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(int(a))  # raw address (device pointer or pinned host)
+
+
+class Context:
+    """One libhvn context (one device, one stream)."""
+
+    def __init__(self, device=0, mode=None, nr_types=None):
+        self._h = ctypes.c_void_p()
+        L = lib()
+        if mode is None:
+            check(L.hvn_create_postproc(int(device), ctypes.byref(self._h)))
+        else:
+            check(L.hvn_create(int(device), mode.encode(), int(nr_types or 0), ctypes.byref(self._h)))
+        self.device = int(device)
+        self.mode = mode
+        self.nr_types = nr_types
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().hvn_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights
+    def param_specs(self):
+        L = lib()
+        out = []
+        name = ctypes.c_char_p()
+        ndim = ctypes.c_int()
+        shape = (ctypes.c_int64 * 4)()
+        for i in range(L.hvn_num_params(self._h)):
+            check(L.hvn_param_info(self._h, i, ctypes.byref(name), ctypes.byref(ndim), shape))
+            out.append((name.value.decode(), tuple(int(shape[j]) for j in range(ndim.value))))
+        return out
+
+    def load_param(self, name, array):
+        a = np.ascontiguousarray(np.asarray(array), dtype=np.float32)
+        shape = (ctypes.c_int64 * 4)(*(list(a.shape) + [0] * (4 - a.ndim)))
+        check(lib().hvn_load_param(self._h, name.encode(), _ptr(a), a.ndim, shape))
+
+    def finalize_weights(self):
+        check(lib().hvn_finalize_weights(self._h))
+
+    def set_option(self, key, value):
+        check(lib().hvn_set_option(self._h, key.encode(), int(value)))
+
+    def counter(self, key):
+        return int(lib().hvn_get_counter(self._h, key.encode()))
+
+    def out_shape(self, h, w):
+        oh, ow, oc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(lib().hvn_out_shape(self._h, int(h), int(w), ctypes.byref(oh), ctypes.byref(ow), ctypes.byref(oc)))
+        return oh.value, ow.value, oc.value
+
+    # ---- host-buffer entry points (what the reference-facing plugin calls)
+    def forward(self, imgs_u8, out=None):
+        x = np.ascontiguousarray(imgs_u8, dtype=np.uint8)
+        B, H, W, C = x.shape
+        assert C == 3
+        oh, ow, oc = self.out_shape(H, W)
+        if out is None:
+            out = np.empty((B, oh, ow, oc), dtype=np.float32)
+        check(lib().hvn_forward(self._h, _ptr(x), B, H, W, _ptr(out)))
+        return out
+
+    def postproc(self, pred, nr_types=None, max_rows=None):
+        p = np.ascontiguousarray(pred, dtype=np.float32)
+        if p.ndim == 3:
+            p = p[None]
+        n, H, W, C = p.shape
+        if max_rows is None:
+            max_rows = max(16, H * W // 64)
+        while True:
+            inst = np.empty((n, H, W), dtype=np.int32)
+            table = np.zeros((n, max_rows, ROW_LEN), dtype=np.int64)
+            nrows = np.zeros((n,), dtype=np.int32)
+            rc = lib().hvn_postproc(self._h, _ptr(p), n, H, W, C, int(nr_types or 0), _ptr(inst), _ptr(table),
+                                    int(max_rows), _ptr(nrows))
+            if rc == -4:  # HVN_ERR_CAPACITY: retry with the exact size
+                max_rows = int(nrows.max())
+                continue
+            check(rc)
+            return inst, table, nrows
+
+    def forward_postproc(self, imgs_u8, want_pred=True, max_rows=None):
+        x = np.ascontiguousarray(imgs_u8, dtype=np.uint8)
+        B, H, W, _ = x.shape
+        oh, ow, oc = self.out_shape(H, W)
+        if max_rows is None:
+            max_rows = max(16, oh * ow // 64)
+        while True:
+            pred = np.empty((B, oh, ow, oc), dtype=np.float32) if want_pred else None
+            inst = np.empty((B, oh, ow), dtype=np.int32)
+            table = np.zeros((B, max_rows, ROW_LEN), dtype=np.int64)
+            nrows = np.zeros((B,), dtype=np.int32)
+            rc = lib().hvn_forward_postproc(self._h, _ptr(x), B, H, W, _ptr(pred), _ptr(inst), _ptr(table),
+                                            int(max_rows), _ptr(nrows))
+            if rc == -4:
+                max_rows = int(nrows.max())
+                continue
+            check(rc)
+            return pred, inst, table, nrows
+
+    # ---- device-pointer entry points + helpers (bench / resident pipelines)
+    def malloc(self, nbytes):
+        p = ctypes.c_void_p()
+        check(lib().hvn_malloc(self._h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def free(self, p):
+        check(lib().hvn_free(self._h, ctypes.c_void_p(p)))
+
+    def malloc_host(self, nbytes):
+        p = ctypes.c_void_p()
+        check(lib().hvn_malloc_host(self._h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def free_host(self, p):
+        check(lib().hvn_free_host(self._h, ctypes.c_void_p(p)))
+
+    def h2d(self, dst, src, nbytes):
+        check(lib().hvn_memcpy_h2d(self._h, _ptr(dst), _ptr(src), int(nbytes)))
+
+    def d2h(self, dst, src, nbytes):
+        check(lib().hvn_memcpy_d2h(self._h, _ptr(dst), _ptr(src), int(nbytes)))
+
+    def sync(self):
+        check(lib().hvn_sync(self._h))
+
+    def timer_start(self):
+        check(lib().hvn_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        check(lib().hvn_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def stage_ms(self, name):
+        ms = ctypes.c_float()
+        check(lib().hvn_stage_ms(self._h, name.encode(), ctypes.byref(ms)))
+        return ms.value
+
+    def forward_dev(self, d_imgs, B, H, W, d_out):
+        check(lib().hvn_forward_dev(self._h, _ptr(d_imgs), B, H, W, _ptr(d_out)))
+
+    def postproc_dev(self, d_pred, n, H, W, C, nr_types, d_inst, d_table, max_rows, d_nrows):
+        check(lib().hvn_postproc_dev(self._h, _ptr(d_pred), n, H, W, C, int(nr_types or 0), _ptr(d_inst),
+                                     _ptr(d_table), int(max_rows), _ptr(d_nrows)))
+
+    def forward_postproc_dev(self, d_imgs, B, H, W, d_pred, d_inst, d_table, max_rows, d_nrows):
+        check(lib().hvn_forward_postproc_dev(self._h, _ptr(d_imgs), B, H, W, _ptr(d_pred), _ptr(d_inst),
+                                             _ptr(d_table), int(max_rows), _ptr(d_nrows)))

@@ -1,0 +1,356 @@
+// C ABI of libhvn (include/hvn.h).  Thin: argument checks, host<->device staging, error mapping.
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/hvn.h"
+#include "cnn.h"
+#include "postproc.h"
+
+using namespace hvn;
+
+static thread_local std::string g_err;
+
+struct hvn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::unique_ptr<Model> model;  // null for post-processing-only contexts
+    Arena pp_arena;                // post-processing workspace
+    Arena io_arena;                // staging for the host-pointer entry points
+    int chunk = 0;
+    int profile = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    float ms_cnn = 0.f, ms_pp = 0.f;
+    long long pp_launches = 0;
+};
+
+#define API_BEGIN try {
+#define API_END                                                     \
+    }                                                               \
+    catch (const hvn::Error &e) { g_err = e.what(); return e.code; } \
+    catch (const std::exception &e) { g_err = e.what(); return HVN_ERR_INVALID; } \
+    return HVN_OK;
+
+static void use(hvn_ctx *c) {
+    HVN_CHECK(c != nullptr, HVN_ERR_INVALID, "null context");
+    HVN_CUDA(cudaSetDevice(c->device));
+}
+
+extern "C" {
+
+int hvn_abi_version(void) { return HVN_ABI_VERSION; }
+const char *hvn_last_error(void) { return g_err.c_str(); }
+
+static int create_common(int device, hvn_ctx **out, const char *mode, int nr_types, bool with_model) {
+    API_BEGIN
+    HVN_CHECK(out != nullptr, HVN_ERR_INVALID, "null out pointer");
+    int ndev = 0;
+    HVN_CUDA(cudaGetDeviceCount(&ndev));
+    HVN_CHECK(device >= 0 && device < ndev, HVN_ERR_INVALID, "no such CUDA device " + std::to_string(device));
+    std::unique_ptr<hvn_ctx> c(new hvn_ctx());
+    c->device = device;
+    HVN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HVN_CUDA(cudaGetDeviceProperties(&prop, device));
+    HVN_CHECK(prop.major == 10, HVN_ERR_CUDA,
+              std::string("libhvn is built for sm_100a only; device is ") + prop.name);
+    if (with_model) c->model.reset(new Model(mode ? mode : "", nr_types));
+    HVN_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) HVN_CUDA(cudaEventCreate(&e));
+    for (auto &e : c->tev) HVN_CUDA(cudaEventCreate(&e));
+    *out = c.release();
+    API_END
+}
+int hvn_create(int device, const char *mode, int nr_types, hvn_ctx **out) {
+    return create_common(device, out, mode, nr_types, true);
+}
+int hvn_create_postproc(int device, hvn_ctx **out) { return create_common(device, out, nullptr, 0, false); }
+
+void hvn_destroy(hvn_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->model.reset();
+    c->pp_arena.release();
+    c->io_arena.release();
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    for (auto &e : c->tev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int hvn_num_params(const hvn_ctx *c) { return (c && c->model) ? (int)c->model->spec.size() : 0; }
+
+int hvn_param_info(const hvn_ctx *c, int index, const char **name, int *ndim, int64_t shape[4]) {
+    API_BEGIN
+    HVN_CHECK(c && c->model, HVN_ERR_STATE, "context has no model");
+    HVN_CHECK(index >= 0 && index < (int)c->model->spec.size(), HVN_ERR_INVALID, "param index out of range");
+    const ParamSpec &s = c->model->spec[index];
+    if (name) *name = s.name.c_str();
+    if (ndim) *ndim = s.ndim;
+    if (shape) for (int i = 0; i < 4; ++i) shape[i] = s.shape[i];
+    API_END
+}
+
+int hvn_load_param(hvn_ctx *c, const char *name, const float *data, int ndim, const int64_t *shape) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    HVN_CHECK(name != nullptr, HVN_ERR_INVALID, "null name");
+    c->model->load(name, data, ndim, shape);
+    API_END
+}
+
+int hvn_finalize_weights(hvn_ctx *c) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    c->model->finalize();
+    API_END
+}
+
+int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
+    API_BEGIN
+    use(c);
+    std::string k = key ? key : "";
+    if (k == "conv_path") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->conv_path = (int)value; }
+    else if (k == "chunk") c->chunk = (int)value;
+    else if (k == "profile") c->profile = (int)value;
+    else throw Error(HVN_ERR_INVALID, "unknown option " + k);
+    API_END
+}
+
+int64_t hvn_get_counter(const hvn_ctx *c, const char *key) {
+    if (!c || !key) return -1;
+    std::string k = key;
+    if (k == "kernel_launches") return (c->model ? c->model->kernel_launches : 0) + c->pp_launches;
+    if (k == "tc_launches") return c->model ? c->model->tc_launches : 0;
+    if (k == "pp_launches") return c->pp_launches;
+    return -1;
+}
+
+int hvn_out_shape(const hvn_ctx *c, int in_h, int in_w, int *out_h, int *out_w, int *out_c) {
+    API_BEGIN
+    HVN_CHECK(c && c->model, HVN_ERR_STATE, "context has no model");
+    int oh, ow, oc;
+    c->model->out_shape(in_h, in_w, oh, ow, oc);
+    if (out_h) *out_h = oh;
+    if (out_w) *out_w = ow;
+    if (out_c) *out_c = oc;
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+static void run_forward(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, float *out) {
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    c->model->forward(imgs, B, H, W, out, c->chunk, c->stream);
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+}
+static void run_postproc(hvn_ctx *c, const float *pred, int n, int H, int W, int C, int nr_types, int32_t *inst,
+                         int64_t *table, int max_rows, int32_t *n_rows) {
+    HVN_CHECK(max_rows >= 1, HVN_ERR_INVALID, "max_rows must be >= 1");
+    HVN_CHECK(nr_types >= 0 && nr_types <= HVN_MAX_TYPES, HVN_ERR_INVALID, "nr_types out of range");
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[2], c->stream));
+    c->pp_launches += postproc_run(c->pp_arena, c->stream, pred, n, H, W, C, nr_types, inst, (long long *)table,
+                                   max_rows, n_rows);
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[3], c->stream));
+}
+static void finish_profile(hvn_ctx *c, bool cnn, bool pp) {
+    if (!c->profile) return;
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    if (cnn) HVN_CUDA(cudaEventElapsedTime(&c->ms_cnn, c->ev[0], c->ev[1]));
+    if (pp) HVN_CUDA(cudaEventElapsedTime(&c->ms_pp, c->ev[2], c->ev[3]));
+}
+static void check_rows(const int32_t *n_rows, int n, int max_rows) {
+    for (int i = 0; i < n; ++i)
+        HVN_CHECK(n_rows[i] <= max_rows, HVN_ERR_CAPACITY,
+                  "instance table too small: map " + std::to_string(i) + " has " + std::to_string(n_rows[i]) +
+                      " instances, max_rows=" + std::to_string(max_rows));
+}
+
+int hvn_forward_dev(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, float *out) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(imgs && out, HVN_ERR_INVALID, "null buffer");
+    run_forward(c, imgs, B, H, W, out);
+    finish_profile(c, true, false);
+    API_END
+}
+
+int hvn_forward(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, float *out) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(imgs && out, HVN_ERR_INVALID, "null buffer");
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    int oh, ow, oc;
+    c->model->out_shape(H, W, oh, ow, oc);
+    size_t in_b = (size_t)B * H * W * 3, out_b = (size_t)B * oh * ow * oc * sizeof(float);
+    c->io_arena.reset();
+    c->io_arena.reserve(in_b + out_b + 1024);
+    uint8_t *d_in = c->io_arena.take<uint8_t>(in_b);
+    float *d_out = c->io_arena.take<float>(out_b / sizeof(float));
+    HVN_CUDA(cudaMemcpyAsync(d_in, imgs, in_b, cudaMemcpyHostToDevice, c->stream));
+    run_forward(c, d_in, B, H, W, d_out);
+    HVN_CUDA(cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    finish_profile(c, true, false);
+    API_END
+}
+
+int hvn_postproc_dev(hvn_ctx *c, const float *pred, int n, int H, int W, int C, int nr_types, int32_t *inst,
+                     int64_t *table, int max_rows, int32_t *n_rows) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(pred && inst && table && n_rows, HVN_ERR_INVALID, "null buffer");
+    run_postproc(c, pred, n, H, W, C, nr_types, inst, table, max_rows, n_rows);
+    finish_profile(c, false, true);
+    API_END
+}
+
+int hvn_postproc(hvn_ctx *c, const float *pred, int n, int H, int W, int C, int nr_types, int32_t *inst,
+                 int64_t *table, int max_rows, int32_t *n_rows) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(pred && inst && table && n_rows, HVN_ERR_INVALID, "null buffer");
+    HVN_CHECK(n >= 1 && H >= 1 && W >= 1, HVN_ERR_INVALID, "empty input");
+    size_t px = (size_t)n * H * W;
+    size_t tb = (size_t)n * max_rows * HVN_ROW_LEN;
+    c->io_arena.reset();
+    c->io_arena.reserve(px * C * 4 + px * 4 + tb * 8 + (size_t)n * 4 + 4096);
+    float *d_pred = c->io_arena.take<float>(px * C);
+    int32_t *d_inst = c->io_arena.take<int32_t>(px);
+    int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    int32_t *d_nr = c->io_arena.take<int32_t>(n);
+    HVN_CUDA(cudaMemcpyAsync(d_pred, pred, px * C * 4, cudaMemcpyHostToDevice, c->stream));
+    run_postproc(c, d_pred, n, H, W, C, nr_types, d_inst, d_tab, max_rows, d_nr);
+    HVN_CUDA(cudaMemcpyAsync(inst, d_inst, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(n_rows, d_nr, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(table, d_tab, tb * 8, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    finish_profile(c, false, true);
+    check_rows(n_rows, n, max_rows);
+    API_END
+}
+
+int hvn_forward_postproc_dev(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, float *pred, int32_t *inst,
+                             int64_t *table, int max_rows, int32_t *n_rows) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(imgs && inst && table && n_rows, HVN_ERR_INVALID, "null buffer");
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    int oh, ow, oc;
+    c->model->out_shape(H, W, oh, ow, oc);
+    float *d_pred = pred;
+    if (!d_pred) {
+        c->io_arena.reset();
+        c->io_arena.reserve((size_t)B * oh * ow * oc * 4 + 1024);
+        d_pred = c->io_arena.take<float>((size_t)B * oh * ow * oc);
+    }
+    run_forward(c, imgs, B, H, W, d_pred);
+    run_postproc(c, d_pred, B, oh, ow, oc, c->model->nr_types, inst, table, max_rows, n_rows);
+    finish_profile(c, true, true);
+    API_END
+}
+
+int hvn_forward_postproc(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, float *pred, int32_t *inst,
+                         int64_t *table, int max_rows, int32_t *n_rows) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(imgs && inst && table && n_rows, HVN_ERR_INVALID, "null buffer");
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    int oh, ow, oc;
+    c->model->out_shape(H, W, oh, ow, oc);
+    size_t in_b = (size_t)B * H * W * 3, px = (size_t)B * oh * ow, tb = (size_t)B * max_rows * HVN_ROW_LEN;
+    c->io_arena.reset();
+    c->io_arena.reserve(in_b + px * oc * 4 + px * 4 + tb * 8 + (size_t)B * 4 + 8192);
+    uint8_t *d_in = c->io_arena.take<uint8_t>(in_b);
+    float *d_pred = c->io_arena.take<float>(px * oc);
+    int32_t *d_inst = c->io_arena.take<int32_t>(px);
+    int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    int32_t *d_nr = c->io_arena.take<int32_t>(B);
+    HVN_CUDA(cudaMemcpyAsync(d_in, imgs, in_b, cudaMemcpyHostToDevice, c->stream));
+    run_forward(c, d_in, B, H, W, d_pred);
+    run_postproc(c, d_pred, B, oh, ow, oc, c->model->nr_types, d_inst, d_tab, max_rows, d_nr);
+    if (pred) HVN_CUDA(cudaMemcpyAsync(pred, d_pred, px * oc * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(inst, d_inst, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(n_rows, d_nr, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(table, d_tab, tb * 8, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    finish_profile(c, true, true);
+    check_rows(n_rows, B, max_rows);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+int hvn_malloc(hvn_ctx *c, size_t bytes, void **p) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(p, HVN_ERR_INVALID, "null out pointer");
+    HVN_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+    API_END
+}
+int hvn_free(hvn_ctx *c, void *p) {
+    API_BEGIN
+    use(c);
+    HVN_CUDA(cudaFree(p));
+    API_END
+}
+int hvn_malloc_host(hvn_ctx *c, size_t bytes, void **p) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(p, HVN_ERR_INVALID, "null out pointer");
+    HVN_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    API_END
+}
+int hvn_free_host(hvn_ctx *c, void *p) {
+    API_BEGIN
+    use(c);
+    HVN_CUDA(cudaFreeHost(p));
+    API_END
+}
+int hvn_memcpy_h2d(hvn_ctx *c, void *dst, const void *src, size_t bytes) {
+    API_BEGIN
+    use(c);
+    HVN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    API_END
+}
+int hvn_memcpy_d2h(hvn_ctx *c, void *dst, const void *src, size_t bytes) {
+    API_BEGIN
+    use(c);
+    HVN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    API_END
+}
+int hvn_sync(hvn_ctx *c) {
+    API_BEGIN
+    use(c);
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    API_END
+}
+int hvn_timer_start(hvn_ctx *c) {
+    API_BEGIN
+    use(c);
+    HVN_CUDA(cudaEventRecord(c->tev[0], c->stream));
+    API_END
+}
+int hvn_timer_stop(hvn_ctx *c, float *ms) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(ms, HVN_ERR_INVALID, "null out pointer");
+    HVN_CUDA(cudaEventRecord(c->tev[1], c->stream));
+    HVN_CUDA(cudaEventSynchronize(c->tev[1]));
+    HVN_CUDA(cudaEventElapsedTime(ms, c->tev[0], c->tev[1]));
+    API_END
+}
+int hvn_stage_ms(const hvn_ctx *c, const char *name, float *ms) {
+    API_BEGIN
+    HVN_CHECK(c && name && ms, HVN_ERR_INVALID, "null argument");
+    std::string k = name;
+    if (k == "cnn") *ms = c->ms_cnn;
+    else if (k == "postproc") *ms = c->ms_pp;
+    else throw Error(HVN_ERR_INVALID, "unknown stage " + k);
+    API_END
+}
+
+}  // extern "C"

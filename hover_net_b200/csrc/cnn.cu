@@ -1,0 +1,462 @@
+// HoVer-Net model state, layer plan and executor.
+//
+// The plan is the reference graph (reference models/hovernet/net_desc.py:17-145,
+// net_utils.py:71-294) re-expressed as a flat list of fused device ops over NHWC buffers:
+//   * post-conv BatchNorm+ReLU (conv1/bn, conv2/bn, conv0/bn, u0/bn) folds into the producing conv's epilogue;
+//   * the pre-activation BN+ReLU of the *next* residual unit (and the group's blk_bna) is a second
+//     output of conv3's epilogue, next to the raw running sum that feeds the residual add;
+//   * dense-block concatenation is a channel-offset write into one buffer, the centre crops are
+//     window offsets (no copies); each dense unit's preact BN is an elementwise pass over that window;
+//   * 2x nearest upsample + skip add is the epilogue of conv_bot / convf;
+//   * TF-"same" padding and valid crops are operand addressing (zero fill outside the view).
+#include "cnn.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace hvn {
+
+static const struct { const char *name; int cin, c1, c3, units, stride; } kGroups[4] = {
+    {"d0", 64, 64, 256, 3, 1}, {"d1", 256, 128, 512, 4, 2}, {"d2", 512, 256, 1024, 6, 2}, {"d3", 1024, 512, 2048, 3, 2}};
+
+Plan::~Plan() {
+    for (void *p : allocs) cudaFree(p);
+}
+
+template <typename T> T *Model::dalloc(size_t n, std::vector<void *> &owner, bool zero) {
+    T *p = nullptr;
+    HVN_CUDA(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    owner.push_back(p);
+    if (zero) HVN_CUDA(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+
+void Model::add_spec(const std::string &name, std::initializer_list<int64_t> shape, bool ignored) {
+    ParamSpec s;
+    s.name = name;
+    s.ndim = (int)shape.size();
+    int i = 0;
+    for (auto v : shape) s.shape[i++] = v;
+    s.ignored = ignored;
+    index[name] = (int)spec.size();
+    spec.push_back(s);
+}
+void Model::add_bn(const std::string &p, int c) {
+    add_spec(p + ".weight", {c});
+    add_spec(p + ".bias", {c});
+    add_spec(p + ".running_mean", {c});
+    add_spec(p + ".running_var", {c});
+    add_spec(p + ".num_batches_tracked", {}, true);
+}
+
+// Checkpoint key inventory == reference state_dict (module registration order).
+Model::Model(const std::string &mode_, int nr_types_) : mode(mode_), nr_types(nr_types_) {
+    HVN_CHECK(mode == "original" || mode == "fast", -1,
+              "Unknown mode `" + mode + "` for HoVerNet. Only support `original` or `fast`.");
+    HVN_CHECK(nr_types >= 0 && nr_types <= HVN_MAX_TYPES, -1, "nr_types out of range");
+    k = mode == "original" ? 5 : 3;
+    add_spec("conv0./.weight", {64, 3, 7, 7});
+    add_bn("conv0.bn", 64);
+    for (auto &g : kGroups) {
+        int unit_in = g.cin;
+        for (int u = 0; u < g.units; ++u) {
+            std::string p = std::string(g.name) + ".units." + std::to_string(u) + ".";
+            if (u != 0) add_bn(p + "preact/bn", unit_in);
+            add_spec(p + "conv1.weight", {g.c1, unit_in, 1, 1});
+            add_bn(p + "conv1/bn", g.c1);
+            add_spec(p + "conv2.weight", {g.c1, g.c1, 3, 3});
+            add_bn(p + "conv2/bn", g.c1);
+            add_spec(p + "conv3.weight", {g.c3, g.c1, 1, 1});
+            unit_in = g.c3;
+        }
+        add_spec(std::string(g.name) + ".shortcut.weight", {g.c3, g.cin, 1, 1});
+        add_bn(std::string(g.name) + ".blk_bna.bn", g.c3);
+    }
+    add_spec("conv_bot.weight", {1024, 2048, 1, 1});
+    if (nr_types > 0) branches_ = {"tp", "np", "hv"};
+    else branches_ = {"np", "hv"};
+    for (auto &b : branches_) {
+        int out_ch = b == "tp" ? nr_types : 2;
+        const struct { const char *u; int cin, ca, units; } us[2] = {{"u3", 1024, 256, 8}, {"u2", 512, 128, 4}};
+        for (auto &u : us) {
+            std::string p = "decoder." + b + "." + u.u + ".";
+            add_spec(p + "conva.weight", {u.ca, u.cin, k, k});
+            int c = u.ca;
+            for (int i = 0; i < u.units; ++i) {
+                std::string q = p + "dense.units." + std::to_string(i) + ".";
+                add_bn(q + "preact_bna/bn", c);
+                add_spec(q + "conv1.weight", {128, c, 1, 1});
+                add_bn(q + "conv1/bn", 128);
+                add_spec(q + "conv2.weight", {32, 32, k, k});
+                c += 32;
+            }
+            add_bn(p + "dense.blk_bna.bn", c);
+            add_spec(p + "convf.weight", {c, c, 1, 1});
+        }
+        add_spec("decoder." + b + ".u1.conva.weight", {64, 256, k, k});
+        add_bn("decoder." + b + ".u0.bn", 64);
+        add_spec("decoder." + b + ".u0.conv.weight", {out_ch, 64, 1, 1});
+        add_spec("decoder." + b + ".u0.conv.bias", {out_ch});
+    }
+    add_spec("upsample2x.unpool_mat", {2, 2}, true);
+}
+
+Model::~Model() {
+    plans_.clear();
+    for (void *p : wallocs_) cudaFree(p);
+}
+
+void Model::load(const std::string &name_in, const float *data, int ndim, const int64_t *shape) {
+    std::string name = name_in;
+    if (name.rfind("module.", 0) == 0) name = name.substr(7);  // run_utils/utils.py:15-29
+    auto it = index.find(name);
+    HVN_CHECK(it != index.end(), -3, "Unexpected key(s) in state_dict: \"" + name + "\"");
+    ParamSpec &s = spec[it->second];
+    if (!s.ignored) {
+        bool same = ndim == s.ndim;
+        for (int i = 0; same && i < ndim; ++i) same = shape[i] == s.shape[i];
+        HVN_CHECK(same, -3, "size mismatch for " + name);
+        HVN_CHECK(data != nullptr, -1, "null data for " + name);
+        host[name].assign(data, data + s.numel());
+    }
+    s.loaded = true;
+    finalized = false;
+}
+
+const std::vector<float> &Model::hostp(const std::string &name) const {
+    auto it = host.find(name);
+    HVN_CHECK(it != host.end(), -3, "Missing key(s) in state_dict: \"" + name + "\"");
+    return it->second;
+}
+
+// OIHW fp32 -> [tap][cout][cin_pad] split fp16 (grouped convs become block-diagonal dense)
+void Model::make_conv(const std::string &name, int groups) {
+    const ParamSpec &s = spec[index.at(name)];
+    const std::vector<float> &w = hostp(name);
+    int O = (int)s.shape[0], I = (int)s.shape[1], KH = (int)s.shape[2], KW = (int)s.shape[3];
+    int cin = I * groups, og = O / groups;
+    ConvWeights cw;
+    cw.taps = KH * KW; cw.kh = KH; cw.kw = KW; cw.cout = O; cw.cin = cin;
+    cw.cin_pad = (cin + 63) / 64 * 64;
+    size_t n = (size_t)cw.taps * O * cw.cin_pad;
+    std::vector<__half> hi(n, __float2half_rn(0.f)), lo(n, __float2half_rn(0.f));
+    for (int o = 0; o < O; ++o) {
+        int g = o / og;
+        for (int i = 0; i < I; ++i)
+            for (int t = 0; t < cw.taps; ++t) {
+                float v = w[((size_t)o * I + i) * cw.taps + t];
+                __half h = __float2half_rn(v);
+                __half l = __float2half_rn(v - __half2float(h));
+                size_t d = ((size_t)t * O + o) * cw.cin_pad + (size_t)g * I + i;
+                hi[d] = h;
+                lo[d] = l;
+            }
+    }
+    cw.hi = dalloc<__half>(n, wallocs_, false);
+    cw.lo = dalloc<__half>(n, wallocs_, false);
+    HVN_CUDA(cudaMemcpy(cw.hi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    HVN_CUDA(cudaMemcpy(cw.lo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    conv_[name] = cw;
+}
+
+// eval-mode BatchNorm2d(eps=1e-5) as y = x*scale + shift
+void Model::make_bn(const std::string &p) {
+    const auto &g = hostp(p + ".weight"), &b = hostp(p + ".bias"), &m = hostp(p + ".running_mean"),
+               &v = hostp(p + ".running_var");
+    int c = (int)g.size();
+    std::vector<float> sc(c), sh(c);
+    for (int i = 0; i < c; ++i) {
+        double s = (double)g[i] / std::sqrt((double)v[i] + 1e-5);
+        sc[i] = (float)s;
+        sh[i] = (float)((double)b[i] - (double)m[i] * s);
+    }
+    BNParams bp;
+    bp.c = c;
+    bp.scale = dalloc<float>(c, wallocs_, false);
+    bp.shift = dalloc<float>(c, wallocs_, false);
+    HVN_CUDA(cudaMemcpy(bp.scale, sc.data(), c * 4, cudaMemcpyHostToDevice));
+    HVN_CUDA(cudaMemcpy(bp.shift, sh.data(), c * 4, cudaMemcpyHostToDevice));
+    bn_[p] = bp;
+}
+
+void Model::finalize() {
+    std::string missing;
+    for (auto &s : spec)
+        if (!s.loaded && !s.ignored) missing += (missing.empty() ? "\"" : ", \"") + s.name + "\"";
+    HVN_CHECK(missing.empty(), -3, "Missing key(s) in state_dict: " + missing);
+    plans_.clear();
+    for (void *p : wallocs_) cudaFree(p);
+    wallocs_.clear();
+    conv_.clear(); bn_.clear(); head_w_.clear(); head_b_.clear();
+    for (auto &s : spec) {
+        if (s.ignored) continue;
+        const std::string &n = s.name;
+        if (n == "conv0./.weight") {
+            const auto &w = hostp(n);  // OIHW [64][3][7][7] -> [ky][kx][ch][64]
+            std::vector<float> t(7 * 7 * 3 * 64);
+            for (int o = 0; o < 64; ++o)
+                for (int ch = 0; ch < 3; ++ch)
+                    for (int ky = 0; ky < 7; ++ky)
+                        for (int kx = 0; kx < 7; ++kx)
+                            t[((ky * 7 + kx) * 3 + ch) * 64 + o] = w[((o * 3 + ch) * 7 + ky) * 7 + kx];
+            conv0_w_ = dalloc<float>(t.size(), wallocs_, false);
+            HVN_CUDA(cudaMemcpy(conv0_w_, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+        } else if (n.size() > 15 && n.compare(n.size() - 15, 15, ".u0.conv.weight") == 0) {
+            const auto &w = hostp(n);
+            float *d = dalloc<float>(w.size(), wallocs_, false);
+            HVN_CUDA(cudaMemcpy(d, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+            head_w_[n.substr(0, n.size() - 7)] = d;
+        } else if (n.size() > 13 && n.compare(n.size() - 13, 13, ".u0.conv.bias") == 0) {
+            const auto &w = hostp(n);
+            float *d = dalloc<float>(w.size(), wallocs_, false);
+            HVN_CUDA(cudaMemcpy(d, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+            head_b_[n.substr(0, n.size() - 5)] = d;
+        } else if (s.ndim == 4) {
+            bool grouped = n.find(".dense.units.") != std::string::npos && n.find("conv2.weight") != std::string::npos;
+            make_conv(n, grouped ? 4 : 1);
+        } else if (n.size() > 13 && n.compare(n.size() - 13, 13, ".running_mean") == 0) {
+            make_bn(n.substr(0, n.size() - 13));
+        }
+    }
+    finalized = true;
+}
+
+void Model::out_shape(int H, int W, int &oh, int &ow, int &oc) const {
+    auto f = [&](int in) {
+        int s = mode == "fast" ? in : in - 6;
+        HVN_CHECK(s >= 8 && s % 8 == 0, -1,
+                  "unsupported patch size " + std::to_string(in) + " for mode `" + mode +
+                      "` (skip connections only line up when the stem output is a multiple of 8)");
+        int d3 = s / 8;
+        int u3 = 2 * d3 - (k - 1) * 9;
+        int u2 = 2 * u3 - (k - 1) * 5;
+        HVN_CHECK(u3 > 0 && u2 > 0, -1, "patch too small for the decoder's valid convolutions");
+        return 2 * u2;
+    };
+    oh = f(H);
+    ow = f(W);
+    oc = nr_types > 0 ? 4 : 3;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+SplitRef sview(const SplitRef &b, int y0, int x0, int h, int w, int c0, int c) {
+    SplitRef v = b;
+    long long off = (long long)y0 * b.sH + (long long)x0 * b.sW + c0;
+    v.hi += off; v.lo += off; v.h = h; v.w = w; v.c = c;
+    return v;
+}
+RawRef rview(const RawRef &b, int y0, int x0, int h, int w, int c0, int c) {
+    RawRef v = b;
+    v.p += (long long)y0 * b.sH + (long long)x0 * b.sW + c0;
+    v.h = h; v.w = w; v.c = c;
+    return v;
+}
+}  // namespace
+
+Plan &Model::plan(int B, int H, int W) {
+    HVN_CHECK(finalized, -5, "weights not finalised (call hvn_finalize_weights)");
+    HVN_CHECK(H == W, -1, "only square patches are supported (reference patch geometry is square)");
+    std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "p" + std::to_string(conv_path);
+    auto it = plans_.find(key);
+    if (it != plans_.end()) return *it->second;
+    std::unique_ptr<Plan> pl(new Plan());
+    Plan &P = *pl;
+    P.B = B; P.H = H; P.W = W;
+    out_shape(H, W, P.oh, P.ow, P.oc);
+
+    auto new_split = [&](int h, int w, int c) {
+        SplitRef r;
+        size_t n = (size_t)B * h * w * c;
+        r.hi = dalloc<__half>(n, P.allocs, true);
+        r.lo = dalloc<__half>(n, P.allocs, true);
+        P.bytes += 2 * n * sizeof(__half);
+        r.sN = (long long)h * w * c; r.sH = w * c; r.sW = c; r.h = h; r.w = w; r.c = c;
+        return r;
+    };
+    auto new_raw = [&](int h, int w, int c) {
+        RawRef r;
+        size_t n = (size_t)B * h * w * c;
+        r.p = dalloc<float>(n, P.allocs, true);
+        P.bytes += n * sizeof(float);
+        r.sN = (long long)h * w * c; r.sH = w * c; r.sW = c; r.h = h; r.w = w; r.c = c;
+        return r;
+    };
+    auto add_conv = [&](const std::string &wname, const SplitRef &a, int stride, int pad, int ho, int wo) -> Op & {
+        Op op;
+        op.kind = Op::CONV;
+        op.name = wname;
+        op.cp.a = a;
+        op.cp.w = conv_.at(wname);
+        op.cp.stride = stride; op.cp.pad_t = pad; op.cp.pad_l = pad;
+        op.cp.B = B; op.cp.ho = ho; op.cp.wo = wo;
+        const ParamSpec &ps = spec[index.at(wname)];
+        op.flops = 2.0 * B * ho * wo * (double)ps.numel();  // grouped conv counted at its true (sparse) size
+        P.ops.push_back(op);
+        return P.ops.back();
+    };
+    auto set_bn = [&](Op &op, const std::string &bnp, const SplitRef &out) {
+        const BNParams &b = bn_.at(bnp);
+        op.cp.out_split = out; op.cp.scale = b.scale; op.cp.shift = b.shift; op.cp.relu = 1;
+    };
+    auto add_bnrelu = [&](const std::string &bnp, const RawRef &in, const SplitRef &out) {
+        Op op;
+        op.kind = Op::BNRELU;
+        op.name = bnp;
+        op.bn_in = in; op.bn_out = out; op.bn = bn_.at(bnp);
+        P.ops.push_back(op);
+    };
+    auto tf_same_lo = [](int size, int ksize, int stride) {  // net_utils.py:51-63
+        int pad = (size % stride == 0) ? std::max(ksize - stride, 0) : std::max(ksize - (size % stride), 0);
+        return pad / 2;
+    };
+
+    // ---- stem
+    const int s0 = mode == "fast" ? H : H - 6;
+    SplitRef X0 = new_split(s0, s0, 64);
+    {
+        Op op;
+        op.kind = Op::CONV0; op.name = "conv0";
+        op.c0_out = X0; op.c0_pad = mode == "fast" ? 3 : 0;
+        op.bn = bn_.at("conv0.bn");
+        op.flops = 2.0 * B * s0 * s0 * 64 * 147;
+        P.ops.push_back(op);
+    }
+    // ---- encoder
+    SplitRef x = X0, D[4];
+    int si = s0, ds[4];
+    for (int gi = 0; gi < 4; ++gi) {
+        const auto &g = kGroups[gi];
+        const std::string gn = g.name;
+        int so = (si + g.stride - 1) / g.stride;
+        RawRef S = new_raw(so, so, g.c3);
+        SplitRef A1 = new_split(si, si, g.c1), A2 = new_split(so, so, g.c1), Pp = new_split(so, so, g.c3);
+        { Op &op = add_conv(gn + ".shortcut.weight", x, g.stride, 0, so, so); op.cp.out_raw = S; }
+        for (int u = 0; u < g.units; ++u) {
+            std::string p = gn + ".units." + std::to_string(u) + ".";
+            const SplitRef &in = u == 0 ? x : Pp;
+            int ri = u == 0 ? si : so, st = u == 0 ? g.stride : 1;
+            SplitRef a1 = A1;  // unit 0 runs conv1 at the group's input resolution; later units reuse the
+                               // same allocation as a compact [ri,ri,c1] tensor
+            if (ri != A1.h) { a1.h = ri; a1.w = ri; a1.sH = ri * g.c1; a1.sN = (long long)ri * ri * g.c1; }
+            { Op &op = add_conv(p + "conv1.weight", in, 1, 0, ri, ri); set_bn(op, p + "conv1/bn", a1); }
+            int lo = tf_same_lo(ri, 3, st);
+            { Op &op = add_conv(p + "conv2.weight", a1, st, lo, so, so); set_bn(op, p + "conv2/bn", A2); }
+            {
+                Op &op = add_conv(p + "conv3.weight", A2, 1, 0, so, so);
+                op.cp.res = S;
+                if (u + 1 < g.units) { op.cp.out_raw = S; set_bn(op, gn + ".units." + std::to_string(u + 1) + ".preact/bn", Pp); }
+                else set_bn(op, gn + ".blk_bna.bn", Pp);
+            }
+        }
+        x = Pp; D[gi] = Pp; ds[gi] = so; si = so;
+    }
+    HVN_CHECK(2 * ds[3] == ds[2] && 2 * ds[2] == ds[1] && 2 * ds[1] == ds[0], -1, "patch size breaks the skip geometry");
+    auto crop_to = [&](const SplitRef &d, int t) {
+        int c = d.h - t;
+        HVN_CHECK(c >= 0, -1, "skip connection smaller than decoder tensor");
+        return sview(d, c / 2, c / 2, t, t, 0, d.c);  // utils.py:11-28 : crop_t = c // 2
+    };
+    // ---- bottleneck: conv_bot, upsample x2, + d2
+    SplitRef U3in = new_split(2 * ds[3], 2 * ds[3], 1024);
+    {
+        Op &op = add_conv("conv_bot.weight", D[3], 1, 0, ds[3], ds[3]);
+        op.cp.up2 = 1; op.cp.skip = crop_to(D[2], 2 * ds[3]); op.cp.out_split = U3in;
+    }
+    // ---- decoder
+    const int km1 = k - 1;
+    const int h3 = 2 * ds[3] - km1, w8 = h3 - 8 * km1;
+    const int h2 = 2 * w8 - km1, w4 = h2 - 4 * km1;
+    const int ho = 2 * w4;
+    HVN_CHECK(ho == P.oh, -1, "internal: output size mismatch");
+    RawRef C3 = new_raw(h3, h3, 512), C2 = new_raw(h2, h2, 256);
+    SplitRef T3 = new_split(h3, h3, 512), T2 = new_split(h2, h2, 256);
+    SplitRef B3 = new_split(h3, h3, 128), B2 = new_split(h2, h2, 128);
+    SplitRef U2in = new_split(2 * w8, 2 * w8, 512), U1in = new_split(ho, ho, 256);
+    SplitRef Hf[3];
+    for (size_t b = 0; b < branches_.size(); ++b) Hf[b] = new_split(ho, ho, 64);
+
+    auto dense = [&](const std::string &pfx, const SplitRef &uin, const RawRef &Cb, const SplitRef &Tb,
+                     const SplitRef &Bb, int hin, int c0, int units, const SplitRef &skip, const SplitRef &out) {
+        int hh = hin - km1;  // after conva (valid)
+        { Op &op = add_conv(pfx + "conva.weight", uin, 1, 0, hh, hh); op.cp.out_raw = rview(Cb, 0, 0, hh, hh, 0, c0); }
+        int c = c0;
+        for (int i = 0; i < units; ++i) {
+            int wi = hh - i * km1, oi = i * km1 / 2, wn = wi - km1, on = oi + km1 / 2;
+            std::string q = pfx + "dense.units." + std::to_string(i) + ".";
+            add_bnrelu(q + "preact_bna/bn", rview(Cb, oi, oi, wi, wi, 0, c), sview(Tb, oi, oi, wi, wi, 0, c));
+            { Op &op = add_conv(q + "conv1.weight", sview(Tb, oi, oi, wi, wi, 0, c), 1, 0, wi, wi);
+              set_bn(op, q + "conv1/bn", sview(Bb, oi, oi, wi, wi, 0, 128)); }
+            { Op &op = add_conv(q + "conv2.weight", sview(Bb, oi, oi, wi, wi, 0, 128), 1, 0, wn, wn);
+              op.cp.out_raw = rview(Cb, on, on, wn, wn, c, 32); }
+            c += 32;
+        }
+        int wl = hh - units * km1, ol = units * km1 / 2;
+        add_bnrelu(pfx + "dense.blk_bna.bn", rview(Cb, ol, ol, wl, wl, 0, c), sview(Tb, ol, ol, wl, wl, 0, c));
+        Op &op = add_conv(pfx + "convf.weight", sview(Tb, ol, ol, wl, wl, 0, c), 1, 0, wl, wl);
+        op.cp.up2 = 1; op.cp.skip = skip; op.cp.out_split = out;
+    };
+
+    Op head;
+    head.kind = Op::HEAD; head.name = "head";
+    head.head.nbranch = (int)branches_.size();
+    head.head.B = B; head.head.h = ho; head.head.w_ = ho; head.head.C = P.oc;
+    for (size_t b = 0; b < branches_.size(); ++b) {
+        const std::string bp = "decoder." + branches_[b] + ".";
+        dense(bp + "u3.", U3in, C3, T3, B3, 2 * ds[3], 256, 8, crop_to(D[1], 2 * w8), U2in);
+        dense(bp + "u2.", U2in, C2, T2, B2, 2 * w8, 128, 4, crop_to(D[0], ho), U1in);
+        { Op &op = add_conv(bp + "u1.conva.weight", U1in, 1, km1 / 2, ho, ho); set_bn(op, bp + "u0.bn", Hf[b]); }
+        head.head.feat[b] = Hf[b];
+        head.head.w[b] = head_w_.at(bp + "u0.conv");
+        head.head.bias[b] = head_b_.at(bp + "u0.conv");
+        head.head.out_ch[b] = branches_[b] == "tp" ? nr_types : 2;
+        head.head.kind[b] = branches_[b] == "tp" ? HEAD_TP : (branches_[b] == "np" ? HEAD_NP : HEAD_HV);
+        head.flops += 2.0 * B * ho * ho * 64 * head.head.out_ch[b];
+    }
+    P.ops.push_back(head);
+
+    for (auto &op : P.ops) {
+        P.flops += op.flops;
+        if (op.kind == Op::CONV && conv_path == 0) tc_plan(op.cp, op.tc);
+    }
+    plans_[key] = std::move(pl);
+    return *plans_[key];
+}
+
+void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int chunk, cudaStream_t s) {
+    HVN_CHECK(finalized, -5, "weights not finalised (call hvn_finalize_weights)");
+    HVN_CHECK(B >= 1, -1, "empty batch");
+    int oh, ow, oc;
+    out_shape(H, W, oh, ow, oc);
+    if (chunk <= 0) chunk = 8;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        int bc = std::min(chunk, B - b0);
+        Plan &P = plan(bc, H, W);
+        for (auto &op : P.ops) {
+            switch (op.kind) {
+            case Op::CONV0:
+                launch_conv0(imgs + (size_t)b0 * H * W * 3, bc, H, W, op.c0_pad, conv0_w_, op.bn.scale, op.bn.shift,
+                             op.c0_out, s);
+                break;
+            case Op::CONV:
+                if (op.tc.ok) { tc_launch(op.cp, op.tc, s); ++tc_launches; }
+                else launch_conv_ref(op.cp, s);
+                break;
+            case Op::BNRELU:
+                launch_bnrelu(op.bn_in, bc, op.bn.scale, op.bn.shift, op.bn_out, s);
+                break;
+            case Op::HEAD: {
+                HeadParams hp = op.head;
+                hp.out = out + (size_t)b0 * oh * ow * oc;
+                launch_head(hp, s);
+                break;
+            }
+            }
+            ++kernel_launches;
+        }
+    }
+    HVN_CUDA(cudaGetLastError());
+}
+
+}  // namespace hvn

@@ -1,0 +1,90 @@
+// HoVer-Net model state + layer plan + executor (host side of the CNN path).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cnn_kernels.h"
+#include "common.cuh"
+
+namespace hvn {
+
+struct ParamSpec {
+    std::string name;
+    int ndim = 0;
+    int64_t shape[4] = {0, 0, 0, 0};
+    bool ignored = false;  // num_batches_tracked / upsample2x.unpool_mat: accepted, unused
+    bool loaded = false;
+    size_t numel() const {
+        size_t n = 1;
+        for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+        return n;
+    }
+};
+
+struct BNParams { float *scale = nullptr, *shift = nullptr; int c = 0; };
+
+struct Op {
+    enum Kind { CONV0, CONV, BNRELU, HEAD } kind = CONV;
+    std::string name;
+    ConvParams cp;          // CONV
+    TcPlan tc;              // CONV: tensor-core plan (ok=false -> referee kernel)
+    // CONV0
+    SplitRef c0_out; int c0_pad = 0;
+    // BNRELU
+    RawRef bn_in; SplitRef bn_out; BNParams bn;
+    // HEAD
+    HeadParams head;
+    double flops = 0;       // 2*MACs of the reference layer (algorithmic)
+};
+
+struct Plan {
+    int B = 0, H = 0, W = 0, oh = 0, ow = 0, oc = 0;
+    std::vector<Op> ops;
+    std::vector<void *> allocs;
+    size_t bytes = 0;
+    double flops = 0;       // algorithmic 2*MACs for B patches
+    ~Plan();
+};
+
+class Model {
+  public:
+    Model(const std::string &mode, int nr_types);
+    ~Model();
+    std::string mode;
+    int nr_types;  // 0 == None
+    int k;         // decoder kernel size
+    std::vector<ParamSpec> spec;
+    std::map<std::string, int> index;
+    std::map<std::string, std::vector<float>> host;
+    bool finalized = false;
+    int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only
+
+    void load(const std::string &name, const float *data, int ndim, const int64_t *shape);
+    void finalize();
+    void out_shape(int H, int W, int &oh, int &ow, int &oc) const;
+    // builds (and caches) the plan for a sub-batch geometry
+    Plan &plan(int B, int H, int W);
+    // runs B patches: imgs u8 [B,H,W,3] (device) -> out f32 [B,oh,ow,oc] (device)
+    void forward(const uint8_t *imgs, int B, int H, int W, float *out, int chunk, cudaStream_t s);
+
+    long long kernel_launches = 0, tc_launches = 0;
+
+  private:
+    std::map<std::string, ConvWeights> conv_;
+    std::map<std::string, BNParams> bn_;
+    float *conv0_w_ = nullptr;
+    std::map<std::string, float *> head_w_, head_b_;
+    std::vector<void *> wallocs_;
+    std::map<std::string, std::unique_ptr<Plan>> plans_;
+    std::vector<std::string> branches_;
+    void add_spec(const std::string &name, std::initializer_list<int64_t> shape, bool ignored = false);
+    void add_bn(const std::string &prefix, int c);
+    const std::vector<float> &hostp(const std::string &name) const;
+    void make_conv(const std::string &name, int groups);
+    void make_bn(const std::string &prefix);
+    template <typename T> T *dalloc(size_t n, std::vector<void *> &owner, bool zero);
+};
+
+}  // namespace hvn

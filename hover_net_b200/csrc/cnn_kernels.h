@@ -1,0 +1,43 @@
+// Launch interfaces of the CNN kernels (conv_ref.cu, conv_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "conv_params.h"
+
+#define HVN_MAX_TYPES 16
+
+namespace hvn {
+
+enum HeadKind { HEAD_TP = 0, HEAD_NP = 1, HEAD_HV = 2 };
+
+struct HeadParams {
+    int nbranch = 0;
+    SplitRef feat[3];
+    const float *w[3] = {nullptr, nullptr, nullptr};     // [out_ch][64]
+    const float *bias[3] = {nullptr, nullptr, nullptr};
+    int out_ch[3] = {0, 0, 0};
+    int kind[3] = {0, 0, 0};
+    int B = 0, h = 0, w_ = 0, C = 0;
+    float *out = nullptr;                                 // [B,h,w,C]
+};
+
+void launch_conv_ref(const ConvParams &P, cudaStream_t s);
+void launch_conv0(const uint8_t *img, int B, int H, int W, int pad, const float *wgt, const float *scale,
+                  const float *shift, const SplitRef &out, cudaStream_t s);
+void launch_bnrelu(const RawRef &in, int B, const float *scale, const float *shift, const SplitRef &out,
+                   cudaStream_t s);
+void launch_head(const HeadParams &P, cudaStream_t s);
+
+// tcgen05 path (conv_tc.cu).  tc_plan() decides eligibility and builds the TMA descriptors once per
+// (layer, buffer geometry); tc_launch() issues the kernel.
+struct TcPlan {
+    bool ok = false;
+    unsigned char tmap_a_hi[128], tmap_a_lo[128], tmap_w_hi[128], tmap_w_lo[128];
+    int bw = 0, bh = 0;          // M-tile = bw x bh output pixels of one image
+    int tiles_x = 0, tiles_y = 0;
+    int block_n = 0;
+    int flat = 0;                // 1x1 stride-1 dense view: M flattened over B*H*W
+};
+bool tc_plan(const ConvParams &P, TcPlan &plan);
+void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s);
+
+}  // namespace hvn

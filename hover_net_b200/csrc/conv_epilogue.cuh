@@ -1,0 +1,65 @@
+// Fused convolution epilogue shared by the referee and the tcgen05 kernels:
+// residual add, raw fp32 store, BN(scale/shift)+ReLU -> split fp16 store, or 2x nearest-neighbour
+// upsample + skip add -> split store (reference net_utils.py:263-265, net_desc.py:133-139).
+#pragma once
+#include "conv_params.h"
+
+namespace hvn {
+
+__device__ __forceinline__ void split_f32(float x, __half &hi, __half &lo) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
+__device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+
+// 4 consecutive output channels c..c+3 of output pixel (n, oy, ox); c % 4 == 0.
+__device__ __forceinline__ void conv_epilogue4(const ConvParams &P, int n, int oy, int ox, int c, float v[4]) {
+    if (P.res.p) {
+        const float4 r = *reinterpret_cast<const float4 *>(P.res.p + n * P.res.sN + (long long)oy * P.res.sH +
+                                                           (long long)ox * P.res.sW + c);
+        v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    if (P.out_raw.p) {
+        float *o = P.out_raw.p + n * P.out_raw.sN + (long long)oy * P.out_raw.sH + (long long)ox * P.out_raw.sW + c;
+        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (P.up2) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int Y = 2 * oy + (d >> 1), X = 2 * ox + (d & 1);
+            long long so = n * P.skip.sN + (long long)Y * P.skip.sH + (long long)X * P.skip.sW + c;
+            long long oo = n * P.out_split.sN + (long long)Y * P.out_split.sH + (long long)X * P.out_split.sW + c;
+            const __half2 *sh = reinterpret_cast<const __half2 *>(P.skip.hi + so);
+            const __half2 *sl = reinterpret_cast<const __half2 *>(P.skip.lo + so);
+            __half2 h01 = sh[0], h23 = sh[1], l01 = sl[0], l23 = sl[1];
+            float t[4] = {v[0] + join_f16(h01.x, l01.x), v[1] + join_f16(h01.y, l01.y),
+                          v[2] + join_f16(h23.x, l23.x), v[3] + join_f16(h23.y, l23.y)};
+            __half oh[4], ol[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i]);
+            *reinterpret_cast<uint2 *>(P.out_split.hi + oo) = *reinterpret_cast<uint2 *>(oh);
+            *reinterpret_cast<uint2 *>(P.out_split.lo + oo) = *reinterpret_cast<uint2 *>(ol);
+        }
+    } else if (P.out_split.hi) {
+        float t[4] = {v[0], v[1], v[2], v[3]};
+        if (P.scale) {
+            const float4 s = *reinterpret_cast<const float4 *>(P.scale + c);
+            const float4 b = *reinterpret_cast<const float4 *>(P.shift + c);
+            t[0] = t[0] * s.x + b.x; t[1] = t[1] * s.y + b.y; t[2] = t[2] * s.z + b.z; t[3] = t[3] * s.w + b.w;
+        }
+        if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = fmaxf(t[i], 0.f);
+        }
+        __half oh[4], ol[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i]);
+        long long oo = n * P.out_split.sN + (long long)oy * P.out_split.sH + (long long)ox * P.out_split.sW + c;
+        *reinterpret_cast<uint2 *>(P.out_split.hi + oo) = *reinterpret_cast<uint2 *>(oh);
+        *reinterpret_cast<uint2 *>(P.out_split.lo + oo) = *reinterpret_cast<uint2 *>(ol);
+    }
+}
+
+}  // namespace hvn

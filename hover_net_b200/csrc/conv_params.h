@@ -1,0 +1,45 @@
+// Parameter blocks shared by the CUDA-core referee convolution (conv_ref.cu) and the tcgen05
+// convolution (conv_tc.cu).  Activations are NHWC.  A "split" tensor stores x as two fp16 planes
+// hi = fp16(x), lo = fp16(x - hi): x ~= hi + lo to ~2^-22 relative, which lets the tensor cores
+// reproduce fp32-grade products with three fp16 MMAs (hi*hi + hi*lo + lo*hi, fp32 accumulate).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace hvn {
+
+struct SplitRef {            // view into a split NHWC buffer, already offset to (n=0,y0,x0,c0)
+    __half *hi = nullptr, *lo = nullptr;
+    long long sN = 0;        // element strides
+    int sH = 0, sW = 0;
+    int h = 0, w = 0, c = 0; // view extent
+};
+struct RawRef {              // view into a raw fp32 NHWC buffer
+    float *p = nullptr;
+    long long sN = 0;
+    int sH = 0, sW = 0;
+    int h = 0, w = 0, c = 0;
+};
+
+struct ConvWeights {         // [tap][cout][cin_pad] fp16 hi/lo, K-major per tap; cin_pad % 64 == 0
+    __half *hi = nullptr, *lo = nullptr;
+    int taps = 0, cout = 0, cin = 0, cin_pad = 0, kh = 0, kw = 0;
+};
+
+struct ConvParams {
+    SplitRef a;              // input view (bounds of the view are the zero-padding bounds)
+    ConvWeights w;
+    int stride = 1, pad_t = 0, pad_l = 0;
+    int B = 0, ho = 0, wo = 0;
+    // epilogue:  v = acc (+ res) ; out_raw = v ; out_split = split(act(v*scale+shift))
+    //            up2: out_split(2y+dy,2x+dx) = split(v + skip(2y+dy,2x+dx))   (no scale/shift)
+    RawRef res;              // optional residual (may alias out_raw element-for-element)
+    RawRef out_raw;          // optional
+    SplitRef out_split;      // optional
+    const float *scale = nullptr, *shift = nullptr;  // per-cout; nullptr => identity
+    int relu = 0;
+    int up2 = 0;
+    SplitRef skip;           // used when up2
+};
+
+}  // namespace hvn

@@ -1,0 +1,115 @@
+/* libhvn -- C ABI of the B200-native HoVer-Net tile-inference + instance post-processing engine.
+ *
+ * Drop-in boundary for the reference's plugin seam (reference infer/base.py:56-78): the three
+ * callables the reference resolves by name map onto these entry points
+ *
+ *   models.hovernet.net_desc.create_model      (net_desc.py:149)   -> hvn_create + hvn_load_param*
+ *   models.hovernet.run_desc.infer_step        (run_desc.py:171)   -> hvn_forward
+ *   models.hovernet.post_proc.process          (post_proc.py:94)   -> hvn_postproc
+ *   (both, with the map never leaving the device)                  -> hvn_forward_postproc
+ *
+ * Plain pointers and sizes only; no torch / Python types.  Every function returns 0 on success
+ * and a negative hvn_status otherwise; hvn_last_error() gives the message of the last failure on
+ * the calling thread.  One context per device; calls on one context are serialised by the caller
+ * (the reference calls run_step from the main thread only, infer/tile.py:308, infer/wsi.py:289).
+ * Buffers are caller-owned.  "_dev" variants take device pointers on the context's device and are
+ * stream-ordered on the context stream (hvn_sync waits for it).
+ */
+#ifndef HVN_H_
+#define HVN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVN_ABI_VERSION 1
+
+typedef enum {
+    HVN_OK = 0,
+    HVN_ERR_INVALID = -1,     /* bad argument / unsupported shape (reference: assert / shape error) */
+    HVN_ERR_CUDA = -2,        /* CUDA runtime or driver failure */
+    HVN_ERR_WEIGHTS = -3,     /* missing / unexpected / mis-shaped checkpoint key (strict load) */
+    HVN_ERR_CAPACITY = -4,    /* caller-provided table too small */
+    HVN_ERR_STATE = -5        /* call order (e.g. forward before weights are finalised) */
+} hvn_status;
+
+/* Instance-table row: one per instance id present in inst_map, ascending id.  int64 x 10.
+ * Replaces the per-instance loop of reference post_proc.py:120-181 (bbox via
+ * misc/utils.py:18-28 with exclusive max; centroid = sum/area == cv2.moments m10/m00, m01/m00;
+ * type vote :161-181).  type/type_count are -1/0 when nr_types == 0. */
+#define HVN_ROW_LEN 10
+enum { HVN_ROW_ID = 0, HVN_ROW_RMIN, HVN_ROW_CMIN, HVN_ROW_RMAX, HVN_ROW_CMAX, HVN_ROW_AREA,
+       HVN_ROW_SUMX, HVN_ROW_SUMY, HVN_ROW_TYPE, HVN_ROW_TYPECNT };
+
+typedef struct hvn_ctx hvn_ctx;
+
+int hvn_abi_version(void);
+const char *hvn_last_error(void);
+
+/* ---- model lifetime: reference create_model(mode, input_ch=3, nr_types, freeze) net_desc.py:149
+ * mode: "original" | "fast".  nr_types: 0 means None (seg-only, 2 decoder branches). */
+int hvn_create(int device, const char *mode, int nr_types, hvn_ctx **out);
+void hvn_destroy(hvn_ctx *ctx);
+
+/* ---- strict checkpoint load: reference infer/base.py:64-68 (`load_state_dict(strict=True)`).
+ * Keys are the reference state_dict names (variables_tf2pytorch.csv col 1); float tensors are
+ * host fp32, contiguous, shapes as in the reference (conv OIHW).  `num_batches_tracked` and
+ * `upsample2x.unpool_mat` are accepted and ignored.  hvn_finalize_weights fails with
+ * HVN_ERR_WEIGHTS if any expected key was not loaded. */
+int hvn_num_params(const hvn_ctx *ctx);
+int hvn_param_info(const hvn_ctx *ctx, int index, const char **name, int *ndim, int64_t shape[4]);
+int hvn_load_param(hvn_ctx *ctx, const char *name, const float *data, int ndim, const int64_t *shape);
+int hvn_finalize_weights(hvn_ctx *ctx);
+
+/* ---- options.  keys: "conv_path" = 0 auto (tcgen05 where eligible), 1 CUDA-core referee only;
+ *                      "chunk" = patches per internal sub-batch (0 = auto). */
+int hvn_set_option(hvn_ctx *ctx, const char *key, int64_t value);
+int64_t hvn_get_counter(const hvn_ctx *ctx, const char *key); /* "kernel_launches", "tc_launches" */
+
+/* ---- geometry of reference HoVerNet.forward (net_desc.py:101-145) for an in_h x in_w patch. */
+int hvn_out_shape(const hvn_ctx *ctx, int in_h, int in_w, int *out_h, int *out_w, int *out_c);
+
+/* ---- infer_step (run_desc.py:171-197): uint8 NHWC [B,H,W,3] RGB 0..255 ->
+ * float32 NHWC [B,h,w,C], C = 3 (np_prob, hv_x, hv_y) or 4 (tp_argmax, np_prob, hv_x, hv_y). */
+int hvn_forward(hvn_ctx *ctx, const uint8_t *imgs_host, int B, int H, int W, float *out_host);
+int hvn_forward_dev(hvn_ctx *ctx, const uint8_t *imgs_dev, int B, int H, int W, float *out_dev);
+
+/* ---- process / __proc_np_hv (post_proc.py:26-90, 94-186) on n_maps independent maps
+ * pred [n_maps,H,W,C] float32 (C = 3, or 4 with nr_types > 0).
+ * inst [n_maps,H,W] int32; table [n_maps,max_rows,HVN_ROW_LEN] int64; n_rows [n_maps] int32.
+ * ctx may be a model context or one made with hvn_create_postproc (no weights needed). */
+int hvn_create_postproc(int device, hvn_ctx **out);
+int hvn_postproc(hvn_ctx *ctx, const float *pred_host, int n_maps, int H, int W, int C, int nr_types,
+                 int32_t *inst_host, int64_t *table_host, int max_rows, int32_t *n_rows_host);
+int hvn_postproc_dev(hvn_ctx *ctx, const float *pred_dev, int n_maps, int H, int W, int C, int nr_types,
+                     int32_t *inst_dev, int64_t *table_dev, int max_rows, int32_t *n_rows_dev);
+
+/* ---- fused tile path: infer_step then process on every patch, pred map stays in HBM.
+ * pred_host / pred_dev may be NULL when the caller does not want the float maps back. */
+int hvn_forward_postproc(hvn_ctx *ctx, const uint8_t *imgs_host, int B, int H, int W, float *pred_host,
+                         int32_t *inst_host, int64_t *table_host, int max_rows, int32_t *n_rows_host);
+int hvn_forward_postproc_dev(hvn_ctx *ctx, const uint8_t *imgs_dev, int B, int H, int W, float *pred_dev,
+                             int32_t *inst_dev, int64_t *table_dev, int max_rows, int32_t *n_rows_dev);
+
+/* ---- device memory / stream helpers for callers without a CUDA binding of their own. */
+int hvn_malloc(hvn_ctx *ctx, size_t bytes, void **dev_ptr);
+int hvn_free(hvn_ctx *ctx, void *dev_ptr);
+int hvn_malloc_host(hvn_ctx *ctx, size_t bytes, void **host_ptr); /* pinned */
+int hvn_free_host(hvn_ctx *ctx, void *host_ptr);
+int hvn_memcpy_h2d(hvn_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int hvn_memcpy_d2h(hvn_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int hvn_sync(hvn_ctx *ctx);
+/* CUDA-event timing on the context stream (the stream every kernel of this library is launched
+ * on): hvn_timer_start .. hvn_timer_stop returns elapsed milliseconds. */
+int hvn_timer_start(hvn_ctx *ctx);
+int hvn_timer_stop(hvn_ctx *ctx, float *ms);
+/* per-stage device time of the last forward / postproc call when option "profile" = 1:
+ * name in {"cnn","postproc"}; returns ms. */
+int hvn_stage_ms(const hvn_ctx *ctx, const char *name, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVN_H_ */

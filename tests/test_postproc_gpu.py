@@ -1,0 +1,88 @@
+"""GPU parity of the post-processing path: libhvn (through the C ABI) vs the CPU oracle, bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from hover_net_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from hover_net_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _check(ctx, P, maps, nr_types):
+    maps = np.stack(maps)
+    inst, table, nrows = ctx.postproc(maps, nr_types)
+    for i in range(maps.shape[0]):
+        oi, ot = P.process_table(maps[i], nr_types)
+        assert np.array_equal(inst[i], oi), "inst_map differs on map %d (%d px)" % (i, int((inst[i] != oi).sum()))
+        assert int(nrows[i]) == ot.shape[0]
+        assert np.array_equal(table[i, : ot.shape[0]], ot)
+
+
+@pytest.mark.parametrize("hw,nt", [((80, 80), None), ((80, 80), 5), ((164, 164), 6), ((270, 270), None),
+                                   ((97, 133), 5), ((33, 47), None)])
+def test_synthetic_nuclei_batches(ctx, oracle_pp, hw, nt):
+    _check(ctx, oracle_pp, [synth.synth_pred_map(hw[0], hw[1], nt, s) for s in range(6)], nt)
+
+
+def test_noise_and_degenerate_maps(ctx, oracle_pp):
+    rng = np.random.default_rng(11)
+    maps = [np.zeros((64, 64, 3), np.float32), np.ones((64, 64, 3), np.float32)]
+    for _ in range(6):  # salt-and-pepper foreground, noisy HV: many tiny components, holes, ties in np
+        m = rng.uniform(-1, 1, (64, 64, 3)).astype(np.float32)
+        m[..., 0] = rng.uniform(0, 1, (64, 64)) ** rng.uniform(0.3, 2.0)
+        maps.append(m)
+    _check(ctx, oracle_pp, maps, None)
+
+
+def test_smooth_random_fields(ctx, oracle_pp):
+    import cv2
+    rng = np.random.default_rng(5)
+    maps = []
+    for _ in range(4):  # CNN-like smooth fields: large irregular blobs with several markers each
+        m = np.stack([cv2.GaussianBlur(rng.standard_normal((164, 164)), (0, 0), s) for s in (6, 4, 4)], -1)
+        m = m / np.abs(m).max((0, 1))
+        m[..., 0] = 0.5 + 0.5 * m[..., 0]
+        maps.append(m.astype(np.float32))
+    _check(ctx, oracle_pp, maps, None)
+
+
+def test_large_tile(ctx, oracle_pp):
+    _check(ctx, oracle_pp, [synth.synth_pred_map(1024, 1024, 6, 3)], 6)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "pp_*.npz"))))
+def test_process_matches_reference_golden(path):
+    from hover_net_b200.models.hovernet.post_proc import process
+    g = np.load(path)
+    nt = None if int(g["nr_types"]) < 0 else int(g["nr_types"])
+    pm = synth.synth_pred_map(int(g["h"]), int(g["w"]), nt, int(g["seed"]))
+    inst, info = process(pm, nr_types=nt, return_centroids=True)
+    assert inst.dtype == np.int32 and np.array_equal(inst, g["inst"])
+    ids = np.array(sorted(info.keys()), dtype=np.int32)
+    assert np.array_equal(ids, g["ids"])
+    for j, i in enumerate(ids):
+        assert np.array_equal(info[i]["bbox"], g["bbox"][j])
+        assert np.array_equal(info[i]["centroid"], g["centroid"][j])
+        assert len(info[i]["contour"]) == g["contour_len"][j]
+        if nt is not None:
+            assert info[i]["type"] == g["type"][j] and info[i]["type_prob"] == g["type_prob"][j]
+
+
+def test_idempotent_and_batch_invariant(ctx):
+    maps = np.stack([synth.synth_pred_map(164, 164, 6, s) for s in range(8)])
+    a = ctx.postproc(maps, 6)
+    b = ctx.postproc(maps, 6)
+    one = ctx.postproc(maps[3], 6)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(a[0][3], one[0][0]) and int(a[2][3]) == int(one[2][0])

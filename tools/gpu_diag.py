@@ -1,0 +1,49 @@
+"""GPU-box diagnostics: per-stage timing and mismatch details (development aid)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from hover_net_b200 import _lib, synth, arch
+from oracle import postproc_oracle as P
+
+def pp():
+    c = _lib.Context(0)
+    for (h, w, nt, n) in [(80, 80, None, 4), (164, 164, 6, 8), (270, 270, None, 2)]:
+        maps = np.stack([synth.synth_pred_map(h, w, nt, s) for s in range(n)])
+        t = time.time(); inst, table, nrows = c.postproc(maps, nt); dt = time.time() - t
+        bad = 0
+        for i in range(n):
+            oi, ot = P.process_table(maps[i], nt)
+            ok_i = np.array_equal(inst[i], oi); ok_t = int(nrows[i]) == len(ot) and np.array_equal(table[i, :len(ot)], ot)
+            if not (ok_i and ok_t):
+                bad += 1
+                print("  MISMATCH map", i, "inst px diff", int((inst[i] != oi).sum()), "rows", int(nrows[i]), len(ot))
+        print("pp %dx%d nt=%s n=%d: bad=%d wall=%.1fms" % (h, w, nt, n, bad, dt * 1e3))
+    c.set_option("profile", 1)
+    maps = np.stack([synth.synth_pred_map(164, 164, 6, s) for s in range(64)])
+    for _ in range(3):
+        c.postproc(maps, 6)
+    print("pp 64x164^2 device ms:", c.stage_ms("postproc"))
+    c.close()
+
+def cnn():
+    import torch
+    from oracle import hovernet_torch as O
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    for mode, nt in (("original", None), ("fast", 6)):
+        g = np.load("tests/golden/cnn_%s_%s.npz" % (mode, nt))
+        x = synth.make_patches(int(g["batch"]), arch.PATCH_GEOMETRY[mode][0], seed=7)
+        net = create_model(mode=mode, nr_types=nt)
+        net.load_state_dict(synth.make_state_dict(mode, nt, 0))
+        for path in (1, 0):
+            net.ctx.set_option("conv_path", path); net.ctx.set_option("profile", 1)
+            out = net.ctx.forward(x)
+            d = np.abs(out[..., -3:] - g["out"][..., -3:])
+            print("cnn %s nt=%s path=%d: max err %.3e mean %.3e  finite=%s  ms=%.2f tc=%d" % (
+                mode, nt, path, d.max(), d.mean(), np.isfinite(out).all(), net.ctx.stage_ms("cnn"), net.ctx.counter("tc_launches")))
+            if nt: print("   tp mismatch frac", (out[..., 0] != g["out"][..., 0]).mean())
+        net.ctx.close()
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["pp", "cnn"]
+    if "pp" in what: pp()
+    if "cnn" in what: cnn()
