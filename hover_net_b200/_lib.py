@@ -25,6 +25,8 @@ def lib():
                                "this package has no CPU fallback")
         L = ctypes.CDLL(LIB_PATH)
         L.hvn_last_error.restype = ctypes.c_char_p
+        L.hvn_debug_log.restype = ctypes.c_char_p
+        L.hvn_debug_log.argtypes = [ctypes.c_void_p]
         L.hvn_get_counter.restype = ctypes.c_int64
         L.hvn_get_counter.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.hvn_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
@@ -98,6 +100,9 @@ class Context:
 
     def set_option(self, key, value):
         check(lib().hvn_set_option(self._h, key.encode(), int(value)))
+
+    def debug_log(self):
+        return lib().hvn_debug_log(self._h).decode("utf-8", "replace")
 
     def counter(self, key):
         return int(lib().hvn_get_counter(self._h, key.encode()))

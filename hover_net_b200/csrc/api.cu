@@ -116,7 +116,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     std::string k = key ? key : "";
     if (k == "conv_path") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->conv_path = (int)value; }
     else if (k == "chunk") c->chunk = (int)value;
-    else if (k == "profile") c->profile = (int)value;
+    else if (k == "profile") { c->profile = (int)value; if (c->model) c->model->profile_ops = value >= 2 ? 1 : 0; }
     else throw Error(HVN_ERR_INVALID, "unknown option " + k);
     API_END
 }
@@ -127,8 +127,15 @@ int64_t hvn_get_counter(const hvn_ctx *c, const char *key) {
     if (k == "kernel_launches") return (c->model ? c->model->kernel_launches : 0) + c->pp_launches;
     if (k == "tc_launches") return c->model ? c->model->tc_launches : 0;
     if (k == "pp_launches") return c->pp_launches;
+    if (c->model) {
+        if (k == "last_flops") return (int64_t)c->model->last_flops;
+        if (k.rfind("launches:", 0) == 0) { auto it = c->model->class_launches.find(k.substr(9)); return it == c->model->class_launches.end() ? 0 : it->second; }
+        if (k.rfind("flops:", 0) == 0) { auto it = c->model->class_flops.find(k.substr(6)); return it == c->model->class_flops.end() ? 0 : (int64_t)it->second; }
+    }
     return -1;
 }
+
+const char *hvn_debug_log(const hvn_ctx *c) { return (c && c->model) ? c->model->debug_log.c_str() : ""; }
 
 int hvn_out_shape(const hvn_ctx *c, int in_h, int in_w, int *out_h, int *out_w, int *out_c) {
     API_BEGIN
@@ -349,6 +356,8 @@ int hvn_stage_ms(const hvn_ctx *c, const char *name, float *ms) {
     std::string k = name;
     if (k == "cnn") *ms = c->ms_cnn;
     else if (k == "postproc") *ms = c->ms_pp;
+    else if (c->model && c->model->class_ms.count(k)) *ms = (float)c->model->class_ms.at(k);
+    else if (k == "conv_tc" || k == "conv_ref" || k == "conv0" || k == "bnrelu" || k == "head") *ms = 0.f;
     else throw Error(HVN_ERR_INVALID, "unknown stage " + k);
     API_END
 }

@@ -240,6 +240,88 @@ void Model::out_shape(int H, int W, int &oh, int &ow, int &oc) const {
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv_path = 2: per-layer self test of the tcgen05 kernel against the CUDA-core referee
+__global__ void k_cmp_raw(const float *a, const float *b, int B, int h, int w, int c, long long sN, int sH, int sW,
+                          unsigned int *out) {
+    long long total = (long long)B * h * w * c;
+    float md = 0.f, mr = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ch = (int)(i % c); long long t = i / c;
+        int x = (int)(t % w); t /= w;
+        int y = (int)(t % h); int n = (int)(t / h);
+        long long o = n * sN + (long long)y * sH + (long long)x * sW + ch;
+        float va = a[o], vb = b[o];
+        float d = fabsf(va - vb);
+        if (!(d == d)) d = 3.0e38f;  // NaN -> huge
+        md = fmaxf(md, d); mr = fmaxf(mr, fabsf(vb));
+    }
+    atomicMax(out + 0, __float_as_uint(md));
+    atomicMax(out + 1, __float_as_uint(mr));
+}
+__global__ void k_cmp_split(const __half *ah, const __half *al, const __half *bh, const __half *bl, int B, int h, int w,
+                            int c, long long sN, int sH, int sW, unsigned int *out) {
+    long long total = (long long)B * h * w * c;
+    float md = 0.f, mr = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ch = (int)(i % c); long long t = i / c;
+        int x = (int)(t % w); t /= w;
+        int y = (int)(t % h); int n = (int)(t / h);
+        long long o = n * sN + (long long)y * sH + (long long)x * sW + ch;
+        float va = __half2float(ah[o]) + __half2float(al[o]), vb = __half2float(bh[o]) + __half2float(bl[o]);
+        float d = fabsf(va - vb);
+        if (!(d == d)) d = 3.0e38f;
+        md = fmaxf(md, d); mr = fmaxf(mr, fabsf(vb));
+    }
+    atomicMax(out + 2, __float_as_uint(md));
+    atomicMax(out + 3, __float_as_uint(mr));
+}
+
+void Model::selftest_conv(const Op &op, cudaStream_t s) {
+    ConvParams a = op.cp, b = op.cp;
+    std::vector<void *> tmp;
+    auto dz = [&](size_t bytes) { void *p = nullptr; HVN_CUDA(cudaMalloc(&p, bytes)); HVN_CUDA(cudaMemsetAsync(p, 0, bytes, s)); tmp.push_back(p); return p; };
+    const int B = op.cp.B;
+    if (op.cp.out_raw.p) {
+        size_t n = (size_t)B * op.cp.out_raw.sN;
+        a.out_raw.p = (float *)dz(n * 4); b.out_raw.p = (float *)dz(n * 4);
+    }
+    if (op.cp.out_split.hi) {
+        size_t n = (size_t)B * op.cp.out_split.sN;
+        a.out_split.hi = (__half *)dz(n * 2); a.out_split.lo = (__half *)dz(n * 2);
+        b.out_split.hi = (__half *)dz(n * 2); b.out_split.lo = (__half *)dz(n * 2);
+    }
+    unsigned int *d_out = (unsigned int *)dz(16);
+    const bool trace = getenv("HVN_TRACE") != nullptr;
+    if (trace) { fprintf(stderr, "[selftest] %s ...\n", op.name.c_str()); fflush(stderr); }
+    tc_launch(a, op.tc, s);
+    launch_conv_ref(b, s);
+    if (op.cp.out_raw.p) {
+        const RawRef &r = op.cp.out_raw;
+        k_cmp_raw<<<296, 256, 0, s>>>(a.out_raw.p, b.out_raw.p, B, r.h, r.w, op.cp.w.cout, r.sN, r.sH, r.sW, d_out);
+    }
+    if (op.cp.out_split.hi) {
+        const SplitRef &r = op.cp.out_split;
+        int hh = op.cp.up2 ? 2 * op.cp.ho : op.cp.ho, ww = op.cp.up2 ? 2 * op.cp.wo : op.cp.wo;
+        k_cmp_split<<<296, 256, 0, s>>>(a.out_split.hi, a.out_split.lo, b.out_split.hi, b.out_split.lo, B, hh, ww,
+                                        op.cp.w.cout, r.sN, r.sH, r.sW, d_out);
+    }
+    unsigned int h_out[4] = {0, 0, 0, 0};
+    HVN_CUDA(cudaMemcpyAsync(h_out, d_out, 16, cudaMemcpyDeviceToHost, s));
+    cudaError_t e = cudaStreamSynchronize(s);
+    float f[4];
+    memcpy(f, h_out, 16);
+    char line[512];
+    snprintf(line, sizeof(line), "%-44s k%dx%d s%d cin%-4d cout%-4d %dx%d flat=%d box=%dx%d bn=%d | raw diff %.3e (ref %.3e) | split diff %.3e (ref %.3e)%s\n",
+             op.name.c_str(), op.cp.w.kh, op.cp.w.kw, op.cp.stride, op.cp.w.cin, op.cp.w.cout, op.cp.ho, op.cp.wo,
+             op.tc.flat, op.tc.bw, op.tc.bh, op.tc.block_n, f[0], f[1], f[2], f[3],
+             e == cudaSuccess ? "" : (std::string("  CUDA ERROR: ") + cudaGetErrorString(e)).c_str());
+    debug_log += line;
+    if (trace) { fputs(line, stderr); fflush(stderr); }
+    for (void *p : tmp) cudaFree(p);
+    HVN_CHECK(e == cudaSuccess, -2, std::string("selftest: ") + cudaGetErrorString(e) + " at " + op.name);
+}
+
+// ------------------------------------------------------------------------------------------------
 namespace {
 SplitRef sview(const SplitRef &b, int y0, int x0, int h, int w, int c0, int c) {
     SplitRef v = b;
@@ -418,7 +500,7 @@ Plan &Model::plan(int B, int H, int W) {
 
     for (auto &op : P.ops) {
         P.flops += op.flops;
-        if (op.kind == Op::CONV && conv_path == 0) tc_plan(op.cp, op.tc);
+        if (op.kind == Op::CONV && conv_path != 1) tc_plan(op.cp, op.tc);
     }
     plans_[key] = std::move(pl);
     return *plans_[key];
@@ -430,33 +512,59 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
     int oh, ow, oc;
     out_shape(H, W, oh, ow, oc);
     if (chunk <= 0) chunk = 8;
+    struct Rec { const char *cls; double flops; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    if (profile_ops) { class_ms.clear(); class_flops.clear(); class_launches.clear(); }
+    last_flops = 0;
+    if (conv_path == 2) debug_log.clear();
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int bc = std::min(chunk, B - b0);
         Plan &P = plan(bc, H, W);
+        last_flops += P.flops;
         for (auto &op : P.ops) {
+            Rec r{nullptr, op.flops, nullptr, nullptr};
+            if (profile_ops) {
+                HVN_CUDA(cudaEventCreate(&r.a));
+                HVN_CUDA(cudaEventCreate(&r.b));
+                HVN_CUDA(cudaEventRecord(r.a, s));
+            }
             switch (op.kind) {
             case Op::CONV0:
                 launch_conv0(imgs + (size_t)b0 * H * W * 3, bc, H, W, op.c0_pad, conv0_w_, op.bn.scale, op.bn.shift,
                              op.c0_out, s);
+                r.cls = "conv0";
                 break;
             case Op::CONV:
-                if (op.tc.ok) { tc_launch(op.cp, op.tc, s); ++tc_launches; }
-                else launch_conv_ref(op.cp, s);
+                if (op.tc.ok && conv_path == 2) selftest_conv(op, s);
+                if (op.tc.ok) { tc_launch(op.cp, op.tc, s); ++tc_launches; r.cls = "conv_tc"; }
+                else { launch_conv_ref(op.cp, s); r.cls = "conv_ref"; }
                 break;
             case Op::BNRELU:
                 launch_bnrelu(op.bn_in, bc, op.bn.scale, op.bn.shift, op.bn_out, s);
+                r.cls = "bnrelu";
                 break;
             case Op::HEAD: {
                 HeadParams hp = op.head;
                 hp.out = out + (size_t)b0 * oh * ow * oc;
                 launch_head(hp, s);
+                r.cls = "head";
                 break;
             }
             }
             ++kernel_launches;
+            if (profile_ops) { HVN_CUDA(cudaEventRecord(r.b, s)); recs.push_back(r); }
         }
     }
     HVN_CUDA(cudaGetLastError());
+    if (profile_ops) {
+        HVN_CUDA(cudaStreamSynchronize(s));
+        for (auto &r : recs) {
+            float ms = 0.f;
+            HVN_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+            class_ms[r.cls] += ms; class_flops[r.cls] += r.flops; class_launches[r.cls] += 1;
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+    }
 }
 
 }  // namespace hvn

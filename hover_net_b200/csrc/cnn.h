@@ -59,7 +59,7 @@ class Model {
     std::map<std::string, int> index;
     std::map<std::string, std::vector<float>> host;
     bool finalized = false;
-    int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only
+    int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only, 2 auto + per-layer self test
 
     void load(const std::string &name, const float *data, int ndim, const int64_t *shape);
     void finalize();
@@ -70,6 +70,13 @@ class Model {
     void forward(const uint8_t *imgs, int B, int H, int W, float *out, int chunk, cudaStream_t s);
 
     long long kernel_launches = 0, tc_launches = 0;
+    // per-kernel-class device time of the last forward() when profile_ops != 0 (CUDA events per launch)
+    int profile_ops = 0;
+    std::map<std::string, double> class_ms, class_flops;
+    std::map<std::string, long long> class_launches;
+    double last_flops = 0;  // algorithmic 2*MACs of the last forward()
+    std::string debug_log;  // conv_path == 2: per-layer tcgen05-vs-referee report of the last forward()
+    void selftest_conv(const Op &op, cudaStream_t s);
 
   private:
     std::map<std::string, ConvWeights> conv_;

@@ -1,6 +1,405 @@
-// tcgen05 convolution path -- placeholder until the kernel lands (plan always declines).
+// tcgen05 convolution for sm_100a: im2col-free NHWC implicit GEMM.
+//
+//   D[pixel, cout] = sum_{tap} sum_{cin}  A_tap[pixel, cin] * W_tap[cout, cin]
+//
+// * A tiles (128 output pixels x 64 input channels, fp16 hi and lo planes) are fetched by TMA
+//   straight from the NHWC activation: a 4-D box (64ch, bw, bh, 1 image) whose origin is shifted
+//   by the filter tap, so zero padding / valid cropping / stride-2 sampling are tensor-map
+//   addressing (out-of-bounds zero fill, elementStrides) -- no im2col buffer exists anywhere.
+//   1x1 stride-1 convolutions over a dense buffer use a flat 2-D [pixels, channels] map instead.
+// * W tiles (BLOCK_N couts x 64 cin, hi and lo) come from the [tap][cout][cin] K-major weight tensor.
+// * Both operands land in 128B-swizzled shared memory; one elected thread issues
+//   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16) three times per K-slice:
+//   hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM  => fp32-grade products from fp16 tensor cores.
+// * Persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM
+//   allocator), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused BN/ReLU/residual/upsample ->
+//   global).  Shared-memory ring of STAGES operand slots; two TMEM accumulator buffers so the epilogue
+//   of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "conv_epilogue.cuh"
 #include "cnn_kernels.h"
+
 namespace hvn {
-bool tc_plan(const ConvParams &, TcPlan &plan) { plan.ok = false; return false; }
-void tc_launch(const ConvParams &, const TcPlan &, cudaStream_t) {}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_3d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_4d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+
+struct TcGeom {
+    int flat, bw, bh, tiles_x, tiles_y, tiles_m, tiles_n, kchunks;
+    long long m_total;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
+
+template <int BLOCK_N> __host__ __device__ constexpr int tc_stage_bytes() { return 2 * A_TILE_BYTES + 2 * BLOCK_N * 128; }
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+          const ConvParams P, const TcGeom G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int STAGE_BYTES = tc_stage_bytes<BLOCK_N>();
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = G.tiles_m * G.tiles_n;
+    const int taps = P.w.taps;
+    const int kiters = taps * G.kchunks;
+    const uint32_t tx_bytes = (uint32_t)(2 * (G.flat ? 128 : G.bw * G.bh) * 128 + 2 * BLOCK_N * 128);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it_global = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tm = tile / G.tiles_n, tn = tile - tm * G.tiles_n;
+                int n_img = 0, y0 = 0, x0 = 0;
+                long long m0 = 0;
+                if (G.flat) m0 = (long long)tm * 128;
+                else {
+                    const int per_img = G.tiles_x * G.tiles_y;
+                    n_img = tm / per_img;
+                    const int r = tm - n_img * per_img;
+                    y0 = (r / G.tiles_x) * G.bh;
+                    x0 = (r - (r / G.tiles_x) * G.tiles_x) * G.bw;
+                }
+                for (int it = 0; it < kiters; ++it, ++it_global) {
+                    const int s = it_global % STAGES;
+                    const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES, b_hi = sa + 2 * A_TILE_BYTES,
+                                   b_lo = b_hi + BLOCK_N * 128;
+                    mbar_expect_tx(full_bar(s), tx_bytes);
+                    const int tap = it / G.kchunks, kc = it - tap * G.kchunks;
+                    if (G.flat) {
+                        tma_2d(a_hi, &tm_a_hi, full_bar(s), kc * 64, (int)m0);
+                        tma_2d(a_lo, &tm_a_lo, full_bar(s), kc * 64, (int)m0);
+                    } else {
+                        const int ky = tap / P.w.kw, kx = tap - ky * P.w.kw;
+                        const int cx = x0 * P.stride + kx - P.pad_l, cy = y0 * P.stride + ky - P.pad_t;
+                        tma_4d(a_hi, &tm_a_hi, full_bar(s), kc * 64, cx, cy, n_img);
+                        tma_4d(a_lo, &tm_a_lo, full_bar(s), kc * 64, cx, cy, n_img);
+                    }
+                    tma_3d(b_hi, &tm_w_hi, full_bar(s), kc * 64, tn * BLOCK_N, tap);
+                    tma_3d(b_lo, &tm_w_lo, full_bar(s), kc * 64, tn * BLOCK_N, tap);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int it_global = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+                const int as = tcount & 1;
+                const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+                mbar_wait(tempty_bar(as), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                for (int it = 0; it < kiters; ++it, ++it_global) {
+                    const int s = it_global % STAGES;
+                    const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_BYTES;
+                    const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
+                                   db_hi = umma_desc(sa + 2 * A_TILE_BYTES),
+                                   db_lo = umma_desc(sa + 2 * A_TILE_BYTES + BLOCK_N * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // 4 x K=16 inside the 64-channel slice: +32 B per step
+                        const uint64_t ko = (uint64_t)(2 * k);
+                        tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                        tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(s));  // slot reusable once these MMAs have read it
+                }
+                tc_commit(tfull_bar(as));     // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;     // accumulator row == pixel index inside the tile
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+            const int tm = tile / G.tiles_n, tn = tile - tm * G.tiles_n;
+            const int as = tcount & 1;
+            const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+            bool valid;
+            int n_img, oy, ox;
+            if (G.flat) {
+                long long m = (long long)tm * 128 + row;
+                valid = m < G.m_total;
+                long long hw = (long long)P.ho * P.wo;
+                n_img = valid ? (int)(m / hw) : 0;
+                int r = valid ? (int)(m - (long long)n_img * hw) : 0;
+                oy = r / P.wo; ox = r - oy * P.wo;
+            } else {
+                const int per_img = G.tiles_x * G.tiles_y;
+                n_img = tm / per_img;
+                const int r = tm - n_img * per_img;
+                const int ty = r / G.tiles_x, tx = r - ty * G.tiles_x;
+                const int py = row / G.bw, px = row - py * G.bw;
+                oy = ty * G.bh + py; ox = tx * G.bw + px;
+                valid = row < G.bw * G.bh && oy < P.ho && ox < P.wo;
+            }
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t r[32];
+                tc_ld32(t_addr + (uint32_t)c0, r);
+                tc_ld_wait();
+                if (c0 + 32 >= BLOCK_N) {  // all TMEM reads of this tile are done: hand the buffer back
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(as));
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                      __uint_as_float(r[j + 3])};
+                        conv_epilogue4(P, n_img, oy, ox, tn * BLOCK_N + c0 + j, v);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+                   const cuuint32_t *box, const cuuint32_t *estr) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    alignas(64) CUtensorMap tm;
+    CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(dst, &tm, sizeof(tm));
+    return true;
+}
+
+static int g_force_block_n = 0;
+void tc_set_block_n(int n) { g_force_block_n = n; }
+
+bool tc_plan(const ConvParams &P, TcPlan &plan) {
+    plan.ok = false;
+    const ConvWeights &w = P.w;
+    if (w.cin_pad % 64 != 0 || w.cout % 32 != 0) return false;
+    if (P.stride != 1 && P.stride != 2) return false;
+    if (P.pad_t != P.pad_l) return false;
+    if ((reinterpret_cast<uintptr_t>(P.a.hi) & 15) || (reinterpret_cast<uintptr_t>(P.a.lo) & 15)) return false;
+    if ((P.a.sW % 8) || (P.a.sH % 8) || (P.a.sN % 8)) return false;
+    int bn = w.cout >= 256 ? 256 : (w.cout >= 128 ? 128 : (w.cout >= 64 ? 64 : 32));
+    if (g_force_block_n && w.cout % g_force_block_n == 0) bn = g_force_block_n;
+    if (w.cout % bn) return false;
+    plan.block_n = bn;
+    const bool dense_rows = (long long)P.a.sW * P.a.w == P.a.sH && (long long)P.a.sH * P.a.h == P.a.sN;
+    plan.flat = (w.taps == 1 && P.stride == 1 && P.pad_t == 0 && dense_rows && P.ho == P.a.h && P.wo == P.a.w) ? 1 : 0;
+    cuuint32_t ones[4] = {1, 1, 1, 1};
+    if (plan.flat) {
+        cuuint64_t dims[2] = {(cuuint64_t)P.a.c, (cuuint64_t)((long long)P.B * P.a.h * P.a.w)};
+        cuuint64_t str[1] = {(cuuint64_t)P.a.sW * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (!encode(plan.tmap_a_hi, P.a.hi, 2, dims, str, box, ones)) return false;
+        if (!encode(plan.tmap_a_lo, P.a.lo, 2, dims, str, box, ones)) return false;
+        plan.bw = 128; plan.bh = 1; plan.tiles_x = plan.tiles_y = 0;
+    } else {
+        // choose the (bw x bh <= 128) pixel rectangle that wastes the fewest accumulator rows
+        int best_bw = 0, best_bh = 0;
+        double best = -1;
+        const int maxb = 256 / P.stride;
+        for (int bw = 1; bw <= std::min(128, maxb); ++bw) {
+            int bh = std::min(128 / bw, maxb);
+            if (bh < 1) continue;
+            for (; bh >= 1; --bh) {
+                double cover = (double)P.ho * P.wo / ((double)cdiv(P.wo, bw) * cdiv(P.ho, bh) * 128.0);
+                if (cover > best + 1e-9) { best = cover; best_bw = bw; best_bh = bh; }
+            }
+        }
+        plan.bw = best_bw; plan.bh = best_bh;
+        plan.tiles_x = cdiv(P.wo, plan.bw); plan.tiles_y = cdiv(P.ho, plan.bh);
+        cuuint64_t dims[4] = {(cuuint64_t)P.a.c, (cuuint64_t)P.a.w, (cuuint64_t)P.a.h, (cuuint64_t)P.B};
+        cuuint64_t str[3] = {(cuuint64_t)P.a.sW * 2, (cuuint64_t)P.a.sH * 2, (cuuint64_t)P.a.sN * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(plan.bw * P.stride), (cuuint32_t)(plan.bh * P.stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)P.stride, (cuuint32_t)P.stride, 1};
+        if (!encode(plan.tmap_a_hi, P.a.hi, 4, dims, str, box, estr)) return false;
+        if (!encode(plan.tmap_a_lo, P.a.lo, 4, dims, str, box, estr)) return false;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout, (cuuint64_t)w.taps};
+        cuuint64_t str[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+        if (!encode(plan.tmap_w_hi, w.hi, 3, dims, str, box, ones)) return false;
+        if (!encode(plan.tmap_w_lo, w.lo, 3, dims, str, box, ones)) return false;
+    }
+    plan.ok = true;
+    return true;
+}
+
+template <int BLOCK_N, int STAGES>
+static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
+    constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 16 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int grid = std::min(G.tiles_m * G.tiles_n, sms);
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
+    memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
+    k_conv_tc<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
+}
+
+void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
+    TcGeom G;
+    G.flat = plan.flat; G.bw = plan.bw; G.bh = plan.bh; G.tiles_x = plan.tiles_x; G.tiles_y = plan.tiles_y;
+    G.kchunks = P.w.cin_pad / 64;
+    G.m_total = (long long)P.B * P.ho * P.wo;
+    G.tiles_m = plan.flat ? cdiv(G.m_total, 128) : P.B * plan.tiles_x * plan.tiles_y;
+    G.tiles_n = P.w.cout / plan.block_n;
+    switch (plan.block_n) {
+    case 256: launch_t<256, 2>(P, plan, G, s); break;
+    case 128: launch_t<128, 3>(P, plan, G, s); break;
+    case 64: launch_t<64, 4>(P, plan, G, s); break;
+    default: launch_t<32, 4>(P, plan, G, s); break;
+    }
+}
+
 }  // namespace hvn

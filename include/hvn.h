@@ -63,10 +63,17 @@ int hvn_param_info(const hvn_ctx *ctx, int index, const char **name, int *ndim, 
 int hvn_load_param(hvn_ctx *ctx, const char *name, const float *data, int ndim, const int64_t *shape);
 int hvn_finalize_weights(hvn_ctx *ctx);
 
-/* ---- options.  keys: "conv_path" = 0 auto (tcgen05 where eligible), 1 CUDA-core referee only;
- *                      "chunk" = patches per internal sub-batch (0 = auto). */
+/* ---- options.  keys: "conv_path" = 0 auto (tcgen05 where eligible), 1 CUDA-core referee only,
+ *                      2 = auto + run every tcgen05 layer against the referee kernel and record the
+ *                      per-layer max differences (hvn_debug_log);
+ *                      "chunk" = patches per internal sub-batch (0 = auto);
+ *                      "profile" = 0 | 1 | 2 (see hvn_stage_ms). */
 int hvn_set_option(hvn_ctx *ctx, const char *key, int64_t value);
-int64_t hvn_get_counter(const hvn_ctx *ctx, const char *key); /* "kernel_launches", "tc_launches" */
+const char *hvn_debug_log(const hvn_ctx *ctx);
+/* counters: "kernel_launches", "tc_launches", "pp_launches", "last_flops" (algorithmic 2*MACs of the
+ * last forward); with option "profile" = 2 also "launches:<class>" and "flops:<class>" for
+ * class in {conv_tc, conv_ref, conv0, bnrelu, head} (see hvn_stage_ms). */
+int64_t hvn_get_counter(const hvn_ctx *ctx, const char *key);
 
 /* ---- geometry of reference HoVerNet.forward (net_desc.py:101-145) for an in_h x in_w patch. */
 int hvn_out_shape(const hvn_ctx *ctx, int in_h, int in_w, int *out_h, int *out_w, int *out_c);
@@ -105,8 +112,10 @@ int hvn_sync(hvn_ctx *ctx);
  * on): hvn_timer_start .. hvn_timer_stop returns elapsed milliseconds. */
 int hvn_timer_start(hvn_ctx *ctx);
 int hvn_timer_stop(hvn_ctx *ctx, float *ms);
-/* per-stage device time of the last forward / postproc call when option "profile" = 1:
- * name in {"cnn","postproc"}; returns ms. */
+/* device time (ms) of the last forward / postproc call.  option "profile" = 1: name in
+ * {"cnn","postproc"} (whole stage, CUDA events on the context stream).  "profile" = 2 additionally
+ * brackets every CNN launch with its own event pair and sums per kernel class:
+ * {"conv_tc","conv_ref","conv0","bnrelu","head"}. */
 int hvn_stage_ms(const hvn_ctx *ctx, const char *name, float *ms);
 
 #ifdef __cplusplus

@@ -47,3 +47,29 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["pp", "cnn"]
     if "pp" in what: pp()
     if "cnn" in what: cnn()
+
+
+def tc(mode="fast", nt=6, B=1):
+    """per-layer tcgen05-vs-referee self test (conv_path=2), then the end-to-end check"""
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    g = np.load("tests/golden/cnn_%s_%s.npz" % (mode, nt))
+    x = synth.make_patches(int(g["batch"]), arch.PATCH_GEOMETRY[mode][0], seed=7)
+    net = create_model(mode=mode, nr_types=nt)
+    net.load_state_dict(synth.make_state_dict(mode, nt, 0))
+    net.ctx.set_option("conv_path", 2)
+    out = net.ctx.forward(x)
+    print(net.ctx.debug_log())
+    d = np.abs(out[..., -3:] - g["out"][..., -3:])
+    print("tc e2e %s: max err %.3e finite=%s tc_launches=%d" % (mode, d.max(), np.isfinite(out).all(), net.ctx.counter("tc_launches")))
+    net.ctx.set_option("conv_path", 0); net.ctx.set_option("profile", 2)
+    for _ in range(2):
+        out = net.ctx.forward(x)
+    for cls in ("conv_tc", "conv_ref", "conv0", "bnrelu", "head"):
+        ms = net.ctx.stage_ms(cls); fl = net.ctx.counter("flops:" + cls); n = net.ctx.counter("launches:" + cls)
+        print("  %-8s %8.3f ms  %4d launches  %8.1f GFLOP  %7.1f TFLOP/s" % (cls, ms, n, fl / 1e9, fl / 1e9 / max(ms, 1e-9)))
+    print("  cnn total ms", net.ctx.stage_ms("cnn"))
+    net.ctx.close()
+
+
+if __name__ == "__main__" and "tc" in sys.argv[1:]:
+    tc(*(sys.argv[sys.argv.index("tc") + 1:sys.argv.index("tc") + 2] or ["fast"]))
