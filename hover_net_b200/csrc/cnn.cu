@@ -512,17 +512,17 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
     int oh, ow, oc;
     out_shape(H, W, oh, ow, oc);
     if (chunk <= 0) chunk = 8;
-    struct Rec { const char *cls; double flops; cudaEvent_t a, b; };
+    struct Rec { const char *cls; double flops; cudaEvent_t a, b; const Op *op; };
     std::vector<Rec> recs;
     if (profile_ops) { class_ms.clear(); class_flops.clear(); class_launches.clear(); }
     last_flops = 0;
-    if (conv_path == 2) debug_log.clear();
+    if (conv_path == 2 || profile_ops >= 2) debug_log.clear();
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int bc = std::min(chunk, B - b0);
         Plan &P = plan(bc, H, W);
         last_flops += P.flops;
         for (auto &op : P.ops) {
-            Rec r{nullptr, op.flops, nullptr, nullptr};
+            Rec r{nullptr, op.flops, nullptr, nullptr, &op};
             if (profile_ops) {
                 HVN_CUDA(cudaEventCreate(&r.a));
                 HVN_CUDA(cudaEventCreate(&r.b));
@@ -562,6 +562,17 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
             float ms = 0.f;
             HVN_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
             class_ms[r.cls] += ms; class_flops[r.cls] += r.flops; class_launches[r.cls] += 1;
+            if (profile_ops >= 2) {
+                char line[384];
+                const Op &o = *r.op;
+                if (o.kind == Op::CONV)
+                    snprintf(line, sizeof(line), "%-44s %-8s k%dx%d s%d cin%-4d cout%-4d out%dx%d box=%dx%d bn=%d %8.4f ms %8.2f GFLOP %7.1f TFLOP/s\n",
+                             o.name.c_str(), r.cls, o.cp.w.kh, o.cp.w.kw, o.cp.stride, o.cp.w.cin, o.cp.w.cout, o.cp.ho, o.cp.wo,
+                             o.tc.bw, o.tc.bh, o.tc.block_n, ms, r.flops / 1e9, r.flops / 1e9 / std::max(ms, 1e-6f));
+                else
+                    snprintf(line, sizeof(line), "%-44s %-8s %8.4f ms\n", o.name.c_str(), r.cls, ms);
+                debug_log += line;
+            }
             cudaEventDestroy(r.a); cudaEventDestroy(r.b);
         }
     }

@@ -39,5 +39,7 @@ struct TcPlan {
 };
 bool tc_plan(const ConvParams &P, TcPlan &plan);
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s);
+void tc_set_block_n(int n);      // tuning knobs (0 = automatic)
+void tc_set_seg_chunks(int n);
 
 }  // namespace hvn

@@ -62,4 +62,72 @@ __device__ __forceinline__ void conv_epilogue4(const ConvParams &P, int n, int o
     }
 }
 
+
+// ---- two-phase form used by the tcgen05 kernel: issue the (independent) global loads of several
+// output pixels first, then finish them, so that the residual / skip read latency overlaps.
+enum { EPI_PLAIN = 0, EPI_RES = 1, EPI_UP2 = 2 };
+
+template <int MODE> struct EpiPre;
+template <> struct EpiPre<EPI_PLAIN> {};
+template <> struct EpiPre<EPI_RES> { float4 r; };
+template <> struct EpiPre<EPI_UP2> { uint2 h[4], l[4]; };
+
+template <int MODE>
+__device__ __forceinline__ void epi_prefetch(const ConvParams &P, int n, int oy, int ox, int c, EpiPre<MODE> &pre) {
+    if constexpr (MODE == EPI_RES) {
+        pre.r = *reinterpret_cast<const float4 *>(P.res.p + n * P.res.sN + (long long)oy * P.res.sH +
+                                                  (long long)ox * P.res.sW + c);
+    } else if constexpr (MODE == EPI_UP2) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int Y = 2 * oy + (d >> 1), X = 2 * ox + (d & 1);
+            long long so = n * P.skip.sN + (long long)Y * P.skip.sH + (long long)X * P.skip.sW + c;
+            pre.h[d] = *reinterpret_cast<const uint2 *>(P.skip.hi + so);
+            pre.l[d] = *reinterpret_cast<const uint2 *>(P.skip.lo + so);
+        }
+    }
+}
+
+__device__ __forceinline__ void store_split4(const SplitRef &o, long long off, const float t[4]) {
+    __half oh[4], ol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i]);
+    *reinterpret_cast<uint2 *>(o.hi + off) = *reinterpret_cast<uint2 *>(oh);
+    *reinterpret_cast<uint2 *>(o.lo + off) = *reinterpret_cast<uint2 *>(ol);
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_finish(const ConvParams &P, int n, int oy, int ox, int c, float v[4],
+                                           const EpiPre<MODE> &pre) {
+    if constexpr (MODE == EPI_RES) { v[0] += pre.r.x; v[1] += pre.r.y; v[2] += pre.r.z; v[3] += pre.r.w; }
+    if (P.out_raw.p) {
+        float *o = P.out_raw.p + n * P.out_raw.sN + (long long)oy * P.out_raw.sH + (long long)ox * P.out_raw.sW + c;
+        *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if constexpr (MODE == EPI_UP2) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int Y = 2 * oy + (d >> 1), X = 2 * ox + (d & 1);
+            const __half *hh = reinterpret_cast<const __half *>(&pre.h[d]);
+            const __half *ll = reinterpret_cast<const __half *>(&pre.l[d]);
+            float t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = v[i] + join_f16(hh[i], ll[i]);
+            store_split4(P.out_split, n * P.out_split.sN + (long long)Y * P.out_split.sH + (long long)X * P.out_split.sW + c, t);
+        }
+    } else if (P.out_split.hi) {
+        float t[4] = {v[0], v[1], v[2], v[3]};
+        if (P.scale) {
+            const float4 s = *reinterpret_cast<const float4 *>(P.scale + c);
+            const float4 b = *reinterpret_cast<const float4 *>(P.shift + c);
+            t[0] = t[0] * s.x + b.x; t[1] = t[1] * s.y + b.y; t[2] = t[2] * s.z + b.z; t[3] = t[3] * s.w + b.w;
+        }
+        if (P.relu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = fmaxf(t[i], 0.f);
+        }
+        store_split4(P.out_split, n * P.out_split.sN + (long long)oy * P.out_split.sH + (long long)ox * P.out_split.sW + c, t);
+    }
+}
+
 }  // namespace hvn

@@ -15,6 +15,11 @@
 //   allocator), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused BN/ReLU/residual/upsample ->
 //   global).  Shared-memory ring of STAGES operand slots; two TMEM accumulator buffers so the epilogue
 //   of tile i overlaps the main loop of tile i+1.
+// * Accumulation precision: the tensor core adds into the fp32 accumulator with truncation, a bias
+//   that grows with the number of MMAs chained into one accumulator (measured on B200: ~4e-5
+//   relative at K=9216).  The K loop is therefore cut into segments of SEG_CHUNKS 64-channel slices
+//   (96 MMAs); each segment accumulates in its own TMEM buffer and the epilogue warps drain it into
+//   fp32 registers (round-to-nearest adds) while the next segment runs in the other buffer.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -98,16 +103,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 
 struct TcGeom {
-    int flat, bw, bh, tiles_x, tiles_y, tiles_m, tiles_n, kchunks;
+    int flat, bw, bh, tiles_x, tiles_y, tiles_m, tiles_n, kchunks, seg;
     long long m_total;
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int EP_WARPS = 8;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 
 template <int BLOCK_N> __host__ __device__ constexpr int tc_stage_bytes() { return 2 * A_TILE_BYTES + 2 * BLOCK_N * 128; }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -122,6 +128,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t ep_base = bar_base + 8u * (2 * STAGES + 4) + 16u;  // 8 warps x [32][32] fp32 transpose tiles (XOR-swizzled)
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,7 +136,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -190,43 +197,50 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int it_global = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-                const int as = tcount & 1;
-                const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
-                mbar_wait(tempty_bar(as), aph ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
-                for (int it = 0; it < kiters; ++it, ++it_global) {
-                    const int s = it_global % STAGES;
-                    const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
-                    mbar_wait(full_bar(s), ph);
+            int it_global = 0, scount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
+                    const int as = scount & 1;
+                    const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
+                    mbar_wait(tempty_bar(as), aph ^ 1u);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + s * STAGE_BYTES;
-                    const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
-                                   db_hi = umma_desc(sa + 2 * A_TILE_BYTES),
-                                   db_lo = umma_desc(sa + 2 * A_TILE_BYTES + BLOCK_N * 128);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                    const int it1 = min(it0 + G.seg, kiters);
+                    for (int it = it0; it < it1; ++it, ++it_global) {
+                        const int s = it_global % STAGES;
+                        const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + s * STAGE_BYTES;
+                        const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
+                                       db_hi = umma_desc(sa + 2 * A_TILE_BYTES),
+                                       db_lo = umma_desc(sa + 2 * A_TILE_BYTES + BLOCK_N * 128);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 4 x K=16 inside the 64-channel slice: +32 B per step
-                        const uint64_t ko = (uint64_t)(2 * k);
-                        tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                        tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
-                        tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
+                        for (int k = 0; k < 4; ++k) {  // 4 x K=16 inside the 64-channel slice: +32 B per step
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
+                        }
+                        tc_commit(empty_bar(s));  // slot reusable once these MMAs have read it
                     }
-                    tc_commit(empty_bar(s));  // slot reusable once these MMAs have read it
+                    tc_commit(tfull_bar(as));     // segment complete -> epilogue warps drain it
                 }
-                tc_commit(tfull_bar(as));     // accumulator complete -> epilogue
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        // warps w and w+4 share a TMEM lane quadrant (w & 3) and split the tile's columns in halves
+        constexpr int CW = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // columns per epilogue warp
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;     // accumulator row == pixel index inside the tile
-        int tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        if (BLOCK_N >= 64 || half == 0) {
+        const int cb = half * CW;
+        float *ep_tile = reinterpret_cast<float *>(smem_raw + (ep_base - smem_u32(smem_raw))) + (warp - 2) * 32 * 32;
+        int scount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / G.tiles_n, tn = tile - tm * G.tiles_n;
-            const int as = tcount & 1;
-            const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
             bool valid;
             int n_img, oy, ox;
             if (G.flat) {
@@ -245,27 +259,66 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 oy = ty * G.bh + py; ox = tx * G.bw + px;
                 valid = row < G.bw * G.bh && oy < P.ho && ox < P.wo;
             }
-            mbar_wait(tfull_bar(as), aph);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t r[32];
-                tc_ld32(t_addr + (uint32_t)c0, r);
-                tc_ld_wait();
-                if (c0 + 32 >= BLOCK_N) {  // all TMEM reads of this tile are done: hand the buffer back
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(as));
-                }
-                if (valid) {
+            float acc[CW];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                      __uint_as_float(r[j + 3])};
-                        conv_epilogue4(P, n_img, oy, ox, tn * BLOCK_N + c0 + j, v);
+            for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+            for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
+                const int as = scount & 1;
+                const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
+                mbar_wait(tfull_bar(as), aph);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + cb);
+#pragma unroll
+                for (int c0 = 0; c0 < CW; c0 += 32) {
+                    uint32_t r[32];
+                    tc_ld32(t_addr + (uint32_t)c0, r);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(as));  // segment drained: the MMA warp may overwrite this buffer
+            }
+            // Transposed write-out: a thread's accumulator row is one pixel x CW channels; storing it directly
+            // would scatter 8-byte pieces over 32 cache lines per instruction.  Each warp passes 32px x 32ch
+            // blocks through its private (XOR-swizzled) shared-memory tile so that 8 lanes cover the 32
+            // channels of one pixel: 128 B of fp32 / 64 B of fp16 contiguous per pixel per instruction.
+            // Residual / skip loads of 4 pixels-per-lane are issued before any of them is consumed.
+            const int sub_px = lane >> 3, sub_g = lane & 7;
+#pragma unroll
+            for (int c0 = 0; c0 < CW; c0 += 32) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4 *>(&ep_tile[lane * 32 + ((g ^ (lane & 7)) << 2)]) =
+                        make_float4(acc[c0 + 4 * g], acc[c0 + 4 * g + 1], acc[c0 + 4 * g + 2], acc[c0 + 4 * g + 3]);
+                __syncwarp();
+                const int ch = tn * BLOCK_N + cb + c0 + sub_g * 4;
+#pragma unroll
+                for (int bt = 0; bt < 2; ++bt) {
+                    int pv[4], pn[4], py[4], px[4];
+                    EpiPre<MODE> pre[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int src = (bt * 4 + u) * 4 + sub_px;
+                        pv[u] = __shfl_sync(0xffffffffu, (int)valid, src);
+                        pn[u] = __shfl_sync(0xffffffffu, n_img, src);
+                        py[u] = __shfl_sync(0xffffffffu, oy, src);
+                        px[u] = __shfl_sync(0xffffffffu, ox, src);
+                        if (pv[u]) epi_prefetch<MODE>(P, pn[u], py[u], px[u], ch, pre[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int src = (bt * 4 + u) * 4 + sub_px;
+                        const float4 t = *reinterpret_cast<const float4 *>(&ep_tile[src * 32 + ((sub_g ^ (src & 7)) << 2)]);
+                        if (pv[u]) {
+                            float v[4] = {t.x, t.y, t.z, t.w};
+                            epi_finish<MODE>(P, pn[u], py[u], px[u], ch, v, pre[u]);
+                        }
                     }
                 }
+                __syncwarp();
             }
+        }
         }
     }
     tc_fence_before();
@@ -309,7 +362,9 @@ static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *d
 }
 
 static int g_force_block_n = 0;
+static int g_seg_chunks = 4;  // 64-channel slices per accumulation segment (4 -> 48 chained MMAs)
 void tc_set_block_n(int n) { g_force_block_n = n; }
+void tc_set_seg_chunks(int n) { g_seg_chunks = n < 1 ? 1 : n; }
 
 bool tc_plan(const ConvParams &P, TcPlan &plan) {
     plan.ok = false;
@@ -319,7 +374,7 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     if (P.pad_t != P.pad_l) return false;
     if ((reinterpret_cast<uintptr_t>(P.a.hi) & 15) || (reinterpret_cast<uintptr_t>(P.a.lo) & 15)) return false;
     if ((P.a.sW % 8) || (P.a.sH % 8) || (P.a.sN % 8)) return false;
-    int bn = w.cout >= 256 ? 256 : (w.cout >= 128 ? 128 : (w.cout >= 64 ? 64 : 32));
+    int bn = w.cout >= 128 ? 128 : (w.cout >= 64 ? 64 : 32);
     if (g_force_block_n && w.cout % g_force_block_n == 0) bn = g_force_block_n;
     if (w.cout % bn) return false;
     plan.block_n = bn;
@@ -366,12 +421,13 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     return true;
 }
 
-template <int BLOCK_N, int STAGES>
-static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
-    constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 16 + 1024;
+template <int BLOCK_N, int STAGES, int MODE>
+static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
+    constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 16 + EP_WARPS * 32 * 32 * 4 + 1024;
+    static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr = false;
     if (!attr) {
-        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     static int sms = 0;
@@ -384,18 +440,25 @@ static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, c
     CUtensorMap a_hi, a_lo, w_hi, w_lo;
     memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
     memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
-    k_conv_tc<BLOCK_N, STAGES><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
+    k_conv_tc<BLOCK_N, STAGES, MODE><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
+}
+
+template <int BLOCK_N, int STAGES>
+static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
+    if (P.up2) launch_tm<BLOCK_N, STAGES, EPI_UP2>(P, plan, G, s);
+    else if (P.res.p) launch_tm<BLOCK_N, STAGES, EPI_RES>(P, plan, G, s);
+    else launch_tm<BLOCK_N, STAGES, EPI_PLAIN>(P, plan, G, s);
 }
 
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     TcGeom G;
     G.flat = plan.flat; G.bw = plan.bw; G.bh = plan.bh; G.tiles_x = plan.tiles_x; G.tiles_y = plan.tiles_y;
     G.kchunks = P.w.cin_pad / 64;
+    G.seg = g_seg_chunks;
     G.m_total = (long long)P.B * P.ho * P.wo;
     G.tiles_m = plan.flat ? cdiv(G.m_total, 128) : P.B * plan.tiles_x * plan.tiles_y;
     G.tiles_n = P.w.cout / plan.block_n;
     switch (plan.block_n) {
-    case 256: launch_t<256, 2>(P, plan, G, s); break;
     case 128: launch_t<128, 3>(P, plan, G, s); break;
     case 64: launch_t<64, 4>(P, plan, G, s); break;
     default: launch_t<32, 4>(P, plan, G, s); break;

@@ -456,50 +456,69 @@ __global__ void k_marker_labels(int N, const int *__restrict__ Lall, const int *
 // at push time.  Flooding never leaves a 4-connected component of the mask and entries of different
 // components never compare in a way that matters, so each surviving blob is flooded independently
 // and exactly by one thread with a private binary heap (same sift rules as heap_general.pxi).
-struct HeapItem { double v; int age; int idx; };
+struct __align__(16) HeapItem { double v; int age; int idx; };
 
 __device__ __forceinline__ bool h_smaller(const HeapItem &a, const HeapItem &b) {
     if (a.v != b.v) return a.v < b.v;
     return a.age < b.age;
 }
-__device__ __forceinline__ void h_push(HeapItem *h, int &n, HeapItem e) {
-    int child = n++;
-    while (child > 0) {
-        int parent = (child + 1) / 2 - 1;
-        HeapItem pe = h[parent];
-        if (!h_smaller(e, pe)) break;
-        h[child] = pe;
-        child = parent;
-    }
-    h[child] = e;
-}
-__device__ __forceinline__ HeapItem h_pop(HeapItem *h, int &n) {
-    HeapItem top = h[0];
-    HeapItem last = h[--n];
-    int i = 0;
-    // sift `last` down from the root (identical comparisons to swap-based sift-down)
-    while (true) {
-        int l = 2 * i + 1, r = l + 1, s = -1;
-        HeapItem best = last;
-        if (l < n) { HeapItem le = h[l]; if (h_smaller(le, best)) { best = le; s = l; } }
-        if (r < n) { HeapItem re = h[r]; if (h_smaller(re, best)) { best = re; s = r; } }
-        if (s < 0) break;
-        h[i] = best;
-        i = s;
-    }
-    if (n > 0) h[i] = last;
-    return top;
-}
 
-__global__ void k_watershed(int H, int W, const double *__restrict__ dist_all, const unsigned char *__restrict__ fg_all,
-                            const int *__restrict__ L1_all, const int *__restrict__ size1_all,
-                            const int *__restrict__ blob_root_all, const int4 *__restrict__ bbox_all, int max_blobs,
-                            HeapItem *__restrict__ heap_all, int *__restrict__ inst_all, PPStats *st) {
+// 4-ary min-heap on (value, age): the first WS_CAP entries (the hot top levels) live in shared memory,
+// the rest in the blob's slice of the global arena.  Keys are a strict total order (apart from
+// equal-valued marker pixels), so the pop sequence -- all that the flood depends on --
+// is the same as for skimage's binary heap.
+constexpr int WS_CAP = 2048;
+struct Heap4 {
+    HeapItem *s, *g;
+    int n;
+    __device__ __forceinline__ HeapItem get(int i) const { return i < WS_CAP ? s[i] : g[i - WS_CAP]; }
+    __device__ __forceinline__ void set(int i, const HeapItem &e) { if (i < WS_CAP) s[i] = e; else g[i - WS_CAP] = e; }
+    __device__ __forceinline__ void push(const HeapItem &e) {
+        int i = n++;
+        while (i > 0) {
+            int p = (i - 1) >> 2;
+            HeapItem pe = get(p);
+            if (!h_smaller(e, pe)) break;
+            set(i, pe);
+            i = p;
+        }
+        set(i, e);
+    }
+    __device__ __forceinline__ HeapItem pop() {
+        HeapItem top = get(0);
+        HeapItem last = get(--n);
+        int i = 0;
+        while (true) {
+            int c = 4 * i + 1;
+            if (c >= n) break;
+            HeapItem best = get(c);
+            int bi = c;
+            int ce = min(c + 4, n);
+            for (int j = c + 1; j < ce; ++j) {
+                HeapItem e = get(j);
+                if (h_smaller(e, best)) { best = e; bi = j; }
+            }
+            if (!h_smaller(best, last)) break;
+            set(i, best);
+            i = bi;
+        }
+        if (n > 0) set(i, last);
+        return top;
+    }
+};
+
+__global__ void __launch_bounds__(32)
+k_watershed(int H, int W, const double *__restrict__ dist_all, const unsigned char *__restrict__ fg_all,
+            const int *__restrict__ L1_all, const int *__restrict__ size1_all,
+            const int *__restrict__ blob_root_all, const int4 *__restrict__ bbox_all, int max_blobs,
+            HeapItem *__restrict__ heap_all, int *inst_all, PPStats *st) {
+    extern __shared__ __align__(16) unsigned char ws_smem[];
     int m = blockIdx.y, N = H * W;
-    int k = blockIdx.x;  // one blob per block, flooded by thread 0 (divergent lanes would serialise)
+    int k = blockIdx.x;  // one blob per warp-sized block; lane 0 runs the (inherently sequential) flood
     int nb = st[m].nblobs;
     if (nb > max_blobs) nb = max_blobs;
-    if (k >= nb || threadIdx.x != 0) return;
+    if (k >= nb) return;
+    const int lane = threadIdx.x;
     const double *dist = dist_all + (size_t)m * N;
     const unsigned char *fg = fg_all + (size_t)m * N;
     const int *L1 = L1_all + (size_t)m * N;
@@ -507,29 +526,197 @@ __global__ void k_watershed(int H, int W, const double *__restrict__ dist_all, c
     int root = blob_root_all[(size_t)m * max_blobs + k];
     int bsize = size1_all[(size_t)m * N + root];
     int4 bb = bbox_all[(size_t)m * max_blobs + k];
-    HeapItem *heap = heap_all + (size_t)m * N + atomicAdd(&st[m].heap_top, bsize);
-    int n = 0;
-    for (int y = bb.x; y <= bb.z; ++y)
-        for (int x = bb.y; x <= bb.w; ++x) {
-            int p = y * W + x;
-            if (L1[p] == root && inst[p] != 0) { HeapItem e = {dist[p], 0, p}; h_push(heap, n, e); }
+    int goff = 0;
+    if (lane == 0) goff = atomicAdd(&st[m].heap_top, bsize);
+    goff = __shfl_sync(0xffffffffu, goff, 0);
+    Heap4 hp;
+    hp.s = reinterpret_cast<HeapItem *>(ws_smem);
+    hp.g = heap_all + (size_t)m * N + goff;
+    hp.n = 0;
+    // marker pixels of this blob, pushed in raster order (age 0); the warp scans the bbox 32 px at a time
+    const int bw = bb.w - bb.y + 1, bh = bb.z - bb.x + 1, area = bw * bh;
+    for (int base = 0; base < area; base += 32) {
+        int i = base + lane;
+        bool is = false;
+        int p = 0;
+        double dv = 0.0;
+        if (i < area) {
+            int yy = bb.x + i / bw, xx = bb.y + i % bw;
+            p = yy * W + xx;
+            is = L1[p] == root && inst[p] != 0;
+            if (is) dv = dist[p];
         }
-    int age = 1;
-    while (n > 0) {
-        HeapItem e = h_pop(heap, n);
-        int y = e.idx / W, x = e.idx - y * W;
-        int lab = inst[e.idx];
-        int q;
-#define HVN_VISIT(cond, qq)                                                      \
-        if (cond) { q = (qq);                                                    \
-            if (fg[q] && inst[q] == 0) { age += 1; inst[q] = lab;                \
-                HeapItem ne = {dist[q], age, q}; h_push(heap, n, ne); } }
-        HVN_VISIT(y > 0, e.idx - W)
-        HVN_VISIT(x > 0, e.idx - 1)
-        HVN_VISIT(x < W - 1, e.idx + 1)
-        HVN_VISIT(y < H - 1, e.idx + W)
-#undef HVN_VISIT
+        unsigned int msk = __ballot_sync(0xffffffffu, is);
+        while (msk) {
+            int src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            int pp = __shfl_sync(0xffffffffu, p, src);
+            double dd = __shfl_sync(0xffffffffu, dv, src);
+            if (lane == 0) { HeapItem e; e.v = dd; e.age = 0; e.idx = pp; hp.push(e); }
+        }
     }
+    if (lane == 0) {
+        int age = 1;
+        while (hp.n > 0) {
+            HeapItem e = hp.pop();
+            const int y = e.idx / W, x = e.idx - y * W;
+            const int lab = inst[e.idx];
+            // neighbour order up, left, right, down; label at push time
+            int q[4] = {y > 0 ? e.idx - W : -1, x > 0 ? e.idx - 1 : -1, x < W - 1 ? e.idx + 1 : -1,
+                        y < H - 1 ? e.idx + W : -1};
+            bool take[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) take[j] = q[j] >= 0 && fg[q[j]] && inst[q[j]] == 0;
+            double dv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dv[j] = take[j] ? dist[q[j]] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (take[j]) {
+                    age += 1;
+                    inst[q[j]] = lab;
+                    HeapItem ne; ne.v = dv[j]; ne.age = age; ne.idx = q[j];
+                    hp.push(ne);
+                }
+        }
+    }
+}
+
+// Patch-sized maps: one CTA per map keeps the per-pixel flood state (-1 outside the mask, 0 unlabelled,
+// >0 label) as int16 in shared memory, plus the hot top of one heap per warp; warps pull blobs of the
+// map from a shared queue (large blobs first).  Same flood, same order -- only the memory it lives in
+// differs from k_watershed, which remains the path for maps too large for shared memory.
+constexpr int WT_WARPS = 8;
+template <typename StateT>
+struct HeapS {  // like Heap4 but with a runtime shared-memory capacity
+    HeapItem *s, *g;
+    int n, cap;
+    __device__ __forceinline__ HeapItem get(int i) const { return i < cap ? s[i] : g[i - cap]; }
+    __device__ __forceinline__ void set(int i, const HeapItem &e) { if (i < cap) s[i] = e; else g[i - cap] = e; }
+    __device__ __forceinline__ void push(const HeapItem &e) {
+        int i = n++;
+        while (i > 0) {
+            int p = (i - 1) >> 2;
+            HeapItem pe = get(p);
+            if (!h_smaller(e, pe)) break;
+            set(i, pe);
+            i = p;
+        }
+        set(i, e);
+    }
+    __device__ __forceinline__ HeapItem pop() {
+        HeapItem top = get(0);
+        HeapItem last = get(--n);
+        int i = 0;
+        while (true) {
+            int c = 4 * i + 1;
+            if (c >= n) break;
+            HeapItem best = get(c);
+            int bi = c;
+            int ce = min(c + 4, n);
+            for (int j = c + 1; j < ce; ++j) {
+                HeapItem e = get(j);
+                if (h_smaller(e, best)) { best = e; bi = j; }
+            }
+            if (!h_smaller(best, last)) break;
+            set(i, best);
+            i = bi;
+        }
+        if (n > 0) set(i, last);
+        return top;
+    }
+};
+
+__global__ void __launch_bounds__(WT_WARPS * 32)
+k_watershed_tile(int H, int W, int heap_cap, const double *__restrict__ dist_all,
+                 const unsigned char *__restrict__ fg_all, const int *__restrict__ L1_all,
+                 const int *__restrict__ size1_all, const int *__restrict__ blob_root_all,
+                 const int4 *__restrict__ bbox_all, int max_blobs, HeapItem *__restrict__ heap_all,
+                 int *__restrict__ inst_all, PPStats *st) {
+    extern __shared__ __align__(16) unsigned char wt_smem[];
+    __shared__ int s_next[2];
+    const int m = blockIdx.x, N = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    short *state = reinterpret_cast<short *>(wt_smem);
+    const size_t state_bytes = ((size_t)N * 2 + 15) & ~(size_t)15;
+    HeapItem *heaps = reinterpret_cast<HeapItem *>(wt_smem + state_bytes);
+    const double *dist = dist_all + (size_t)m * N;
+    const unsigned char *fg = fg_all + (size_t)m * N;
+    const int *L1 = L1_all + (size_t)m * N;
+    int *inst = inst_all + (size_t)m * N;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) state[p] = fg[p] ? (short)inst[p] : (short)-1;
+    if (threadIdx.x < 2) s_next[threadIdx.x] = 0;
+    __syncthreads();
+    int nb = st[m].nblobs;
+    if (nb > max_blobs) nb = max_blobs;
+    HeapS<short> hp;
+    hp.s = heaps + (size_t)warp * heap_cap;
+    hp.cap = heap_cap;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: blobs >= 512 px (long floods start first), pass 1: the rest
+        while (true) {
+            int k = 0;
+            if (lane == 0) k = atomicAdd(&s_next[pass], 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= nb) break;
+            const int root = blob_root_all[(size_t)m * max_blobs + k];
+            const int bsize = size1_all[(size_t)m * N + root];
+            if ((bsize >= 512) != (pass == 0)) continue;
+            const int4 bb = bbox_all[(size_t)m * max_blobs + k];
+            int goff = 0;
+            if (lane == 0) goff = atomicAdd(&st[m].heap_top, bsize);
+            goff = __shfl_sync(0xffffffffu, goff, 0);
+            hp.g = heap_all + (size_t)m * N + goff;
+            hp.n = 0;
+            const int bw = bb.w - bb.y + 1, bh = bb.z - bb.x + 1, area = bw * bh;
+            for (int base = 0; base < area; base += 32) {
+                int i = base + lane;
+                bool is = false;
+                int p = 0;
+                double dv = 0.0;
+                if (i < area) {
+                    int yy = bb.x + i / bw, xx = bb.y + i % bw;
+                    p = yy * W + xx;
+                    is = state[p] > 0 && L1[p] == root;
+                    if (is) dv = dist[p];
+                }
+                unsigned int msk = __ballot_sync(0xffffffffu, is);
+                while (msk) {
+                    int src = __ffs(msk) - 1;
+                    msk &= msk - 1;
+                    int pp = __shfl_sync(0xffffffffu, p, src);
+                    double dd = __shfl_sync(0xffffffffu, dv, src);
+                    if (lane == 0) { HeapItem e; e.v = dd; e.age = 0; e.idx = pp; hp.push(e); }
+                }
+            }
+            if (lane == 0) {
+                int age = 1;
+                while (hp.n > 0) {
+                    HeapItem e = hp.pop();
+                    const int y = e.idx / W, x = e.idx - y * W;
+                    const short lab = state[e.idx];
+                    int q[4] = {y > 0 ? e.idx - W : -1, x > 0 ? e.idx - 1 : -1, x < W - 1 ? e.idx + 1 : -1,
+                                y < H - 1 ? e.idx + W : -1};
+                    bool take[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) take[j] = q[j] >= 0 && state[q[j]] == 0;
+                    double dv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dv[j] = take[j] ? __ldg(dist + q[j]) : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (take[j]) {
+                            age += 1;
+                            state[q[j]] = lab;
+                            HeapItem ne; ne.v = dv[j]; ne.age = age; ne.idx = q[j];
+                            hp.push(ne);
+                        }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < N; p += blockDim.x) { short v = state[p]; inst[p] = v > 0 ? (int)v : 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -707,8 +894,25 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
     L(k_assign_ids<<<gr, TPB, 0, stream>>>(H, W, b.L2, b.rowcnt, b.id3));
     L(k_marker_labels<<<g1, TPB, 0, stream>>>(N, b.L2, b.size3, b.id3, b.fg, inst));
     // flood
-    L(k_watershed<<<dim3((unsigned)b.max_blobs, (unsigned)n), 32, 0, stream>>>(
-        H, W, b.dist, b.fg, b.L1, b.size1, b.blob_root, (int4 *)b.bbox, b.max_blobs, (HeapItem *)b.heap, inst, st));
+    {
+        // patch-sized maps: per-map CTA with the flood state in shared memory; otherwise the generic kernel
+        const size_t budget = 200 * 1024, state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15);
+        long long cap = state_bytes < budget ? (long long)((budget - state_bytes) / (WT_WARPS * sizeof(HeapItem))) : 0;
+        if (cap > 4096) cap = 4096;
+        if (cap >= 256 && b.max_ids < 32000) {
+            static bool attr = false;
+            if (!attr) {
+                HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 1024));
+                attr = true;
+            }
+            size_t smem = state_bytes + (size_t)cap * WT_WARPS * sizeof(HeapItem);
+            L(k_watershed_tile<<<n, WT_WARPS * 32, smem, stream>>>(H, W, (int)cap, b.dist, b.fg, b.L1, b.size1, b.blob_root,
+                                                             (int4 *)b.bbox, b.max_blobs, (HeapItem *)b.heap, inst, st));
+        } else {
+            L(k_watershed<<<dim3((unsigned)b.max_blobs, (unsigned)n), 32, WS_CAP * sizeof(HeapItem), stream>>>(
+                H, W, b.dist, b.fg, b.L1, b.size1, b.blob_root, (int4 *)b.bbox, b.max_blobs, (HeapItem *)b.heap, inst, st));
+        }
+    }
     // table
     L(k_table_accum<<<g1, TPB, 0, stream>>>(H, W, inst, pred, C, nr_types, (InstAcc *)b.acc, b.tcnt, b.max_ids));
     L(k_table_rows<<<n, 1024, 0, stream>>>((InstAcc *)b.acc, b.tcnt, nr_types, b.max_ids, table, max_rows, n_rows, st));

@@ -49,27 +49,84 @@ if __name__ == "__main__":
     if "cnn" in what: cnn()
 
 
-def tc(mode="fast", nt=6, B=1):
+def tc(mode="fast", nt=6, verbose=False):
     """per-layer tcgen05-vs-referee self test (conv_path=2), then the end-to-end check"""
+    import re
     from hover_net_b200.models.hovernet.net_desc import create_model
+    nt = {"fast": 6, "original": 5}[mode]
     g = np.load("tests/golden/cnn_%s_%s.npz" % (mode, nt))
     x = synth.make_patches(int(g["batch"]), arch.PATCH_GEOMETRY[mode][0], seed=7)
     net = create_model(mode=mode, nr_types=nt)
     net.load_state_dict(synth.make_state_dict(mode, nt, 0))
-    net.ctx.set_option("conv_path", 2)
-    out = net.ctx.forward(x)
-    print(net.ctx.debug_log())
-    d = np.abs(out[..., -3:] - g["out"][..., -3:])
-    print("tc e2e %s: max err %.3e finite=%s tc_launches=%d" % (mode, d.max(), np.isfinite(out).all(), net.ctx.counter("tc_launches")))
-    net.ctx.set_option("conv_path", 0); net.ctx.set_option("profile", 2)
-    for _ in range(2):
+    for seg in (8, 4, 16):
+        net.ctx.set_option("tc_seg_chunks", seg)
+        net.ctx.set_option("conv_path", 2)
         out = net.ctx.forward(x)
-    for cls in ("conv_tc", "conv_ref", "conv0", "bnrelu", "head"):
-        ms = net.ctx.stage_ms(cls); fl = net.ctx.counter("flops:" + cls); n = net.ctx.counter("launches:" + cls)
-        print("  %-8s %8.3f ms  %4d launches  %8.1f GFLOP  %7.1f TFLOP/s" % (cls, ms, n, fl / 1e9, fl / 1e9 / max(ms, 1e-9)))
-    print("  cnn total ms", net.ctx.stage_ms("cnn"))
+        log = net.ctx.debug_log().strip().split("\n")
+        rows = []
+        for ln in log:
+            m = re.findall(r"diff ([0-9.e+-]+) \(ref ([0-9.e+-]+)\)", ln)
+            rel = max(float(d) / max(float(r), 1e-30) for d, r in m if float(r) > 0) if m else 0
+            rows.append((rel, ln))
+        rows.sort(reverse=True)
+        if verbose:
+            print("\n".join(log))
+        print("seg=%d: worst layers by relative diff:" % seg)
+        for rel, ln in rows[:4]:
+            print("   rel %.2e | %s" % (rel, ln[:150]))
+        d = np.abs(out[..., -3:] - g["out"][..., -3:])
+        print("seg=%d tc e2e %s: max err %.3e mean %.3e finite=%s tc_launches=%d" % (seg, mode, d.max(), d.mean(), np.isfinite(out).all(), net.ctx.counter("tc_launches")))
+        net.ctx.set_option("conv_path", 0); net.ctx.set_option("profile", 2)
+        for _ in range(2):
+            out = net.ctx.forward(x)
+        for cls in ("conv_tc", "conv_ref", "conv0", "bnrelu", "head"):
+            ms = net.ctx.stage_ms(cls); fl = net.ctx.counter("flops:" + cls); n = net.ctx.counter("launches:" + cls)
+            print("  %-8s %8.3f ms  %4d launches  %8.1f GFLOP  %7.1f TFLOP/s" % (cls, ms, n, fl / 1e9, fl / 1e9 / max(ms, 1e-9)))
+        print("  cnn total ms", net.ctx.stage_ms("cnn"), "batch", x.shape[0])
+        net.ctx.set_option("profile", 0)
     net.ctx.close()
 
 
 if __name__ == "__main__" and "tc" in sys.argv[1:]:
     tc(*(sys.argv[sys.argv.index("tc") + 1:sys.argv.index("tc") + 2] or ["fast"]))
+
+
+def layers(mode="fast", B=8):
+    """per-layer device time at batch B (profile=3)"""
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    nt = {"fast": 6, "original": 5}[mode]
+    x = synth.make_patches(B, arch.PATCH_GEOMETRY[mode][0], seed=7)
+    net = create_model(mode=mode, nr_types=nt)
+    net.load_state_dict(synth.make_state_dict(mode, nt, 0))
+    net.ctx.set_option("chunk", B)
+    net.ctx.forward(x)
+    net.ctx.set_option("profile", 3)
+    net.ctx.forward(x)
+    print(net.ctx.debug_log())
+    for cls in ("conv_tc", "conv_ref", "conv0", "bnrelu", "head"):
+        ms = net.ctx.stage_ms(cls); fl = net.ctx.counter("flops:" + cls); n = net.ctx.counter("launches:" + cls)
+        print("  %-8s %8.3f ms  %4d launches  %8.1f GFLOP  %7.1f TFLOP/s" % (cls, ms, n, fl / 1e9, fl / 1e9 / max(ms, 1e-9)))
+    print("  cnn total ms", net.ctx.stage_ms("cnn"), "batch", B)
+    net.ctx.close()
+
+
+if __name__ == "__main__" and "layers" in sys.argv[1:]:
+    i = sys.argv.index("layers")
+    layers(sys.argv[i + 1] if len(sys.argv) > i + 1 else "fast", int(sys.argv[i + 2]) if len(sys.argv) > i + 2 else 8)
+
+
+def cpuf():
+    """torch CPU forward time vs thread count (to pick a fair reference-arm setting)"""
+    import torch
+    from oracle import hovernet_torch as O
+    sd = O.to_torch_state_dict(synth.make_state_dict("fast", 6, 0))
+    x = synth.make_patches(4, 256, seed=1)
+    for th in (8, 16, 32, 64, 128):
+        torch.set_num_threads(th)
+        O.infer_step(x[:1], sd, "fast", 6)
+        t = time.time(); O.infer_step(x, sd, "fast", 6); dt = time.time() - t
+        print("torch cpu threads=%d: %.3f s/patch (batch 4)" % (th, dt / 4))
+
+
+if __name__ == "__main__" and "cpuf" in sys.argv[1:]:
+    cpuf()
