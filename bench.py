@@ -127,7 +127,8 @@ def run_reference(args):
     P.build()
     mode, nt = args.mode, args.nr_types
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads = min(cores, args.cpu_threads)  # torch's CPU conv degrades badly past ~32 threads
+    torch.set_num_threads(threads)
     sd = O.to_torch_state_dict(synth.make_state_dict(mode, nt, seed=0))
     sample = args.ref_sample
     x = synth.make_patches(sample, 256 if mode == "fast" else 270, seed=1)
@@ -151,9 +152,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, note="bounded sample of %d patches per step" % sample),
-        "cpu_baseline": {"value": val, "unit": "tiles/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "tiles/s", "cores": max(threads, workers), "host_cores": cores, "kind": "port",
                          "sample": "%d patches/step: torch fp32 forward on %s (%d threads) + oracle post-proc in a "
-                                   "%d-process pool" % (sample, fwd_dev, cores, workers)},
+                                   "%d-process pool" % (sample, fwd_dev, threads, workers)},
         "e2e": {"value": val, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -282,7 +283,9 @@ def run_ours(args):
     nr_e2e = np_from_addr(h_nr, (B,), np.int32).copy()
 
     # ---- per-kernel-class profile pass (untimed): per-launch CUDA events
+    ctx.set_option("branch_streams", 0)  # isolated kernels: per-launch event times must not overlap
     ctx.set_option("profile", 2)
+    step_resident()
     step_resident()
     ctx.sync()
     prof = {}
@@ -293,6 +296,7 @@ def run_ours(args):
     prof["cnn_total_ms"] = ctx.stage_ms("cnn")
     flops_step = float(ctx.counter("last_flops"))
     ctx.set_option("profile", 0)
+    ctx.set_option("branch_streams", 1)
 
     # sanity: resident and e2e paths agree
     same = bool(np.array_equal(d_inst.cpu().numpy(), inst_e2e)) and bool(np.array_equal(d_nr.cpu().numpy(), nr_e2e))
@@ -354,7 +358,8 @@ def cpu_baseline(args):
     from oracle import postproc_oracle as P
     P.build()
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads = min(cores, args.cpu_threads)
+    torch.set_num_threads(threads)
     mode, nt = args.mode, args.nr_types
     sd = O.to_torch_state_dict(synth.make_state_dict(mode, nt, seed=0))
     n = args.cpu_sample
@@ -376,9 +381,9 @@ def cpu_baseline(args):
     pp1 = (time.perf_counter() - t3) / min(n, 8)
     if pool:
         pool.close()
-    return {"value": n / (t2 - t0), "unit": "tiles/s", "cores": cores, "kind": "port",
+    return {"value": n / (t2 - t0), "unit": "tiles/s", "cores": max(threads, workers), "host_cores": cores, "kind": "port",
             "sample": "%d patches: torch fp32 CPU forward (%d threads) %.2fs + oracle post-proc in a %d-process pool "
-                      "%.3fs; single-core post-proc %.2f ms/tile" % (n, cores, t1 - t0, workers, t2 - t1, pp1 * 1e3),
+                      "%.3fs; single-core post-proc %.2f ms/tile" % (n, threads, t1 - t0, workers, t2 - t1, pp1 * 1e3),
             "forward_s_per_tile": (t1 - t0) / n, "postproc_ms_per_tile_1core": pp1 * 1e3}
 
 
@@ -393,8 +398,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--conv-path", type=int, default=None)
-    ap.add_argument("--cpu-sample", type=int, default=16)
-    ap.add_argument("--ref-sample", type=int, default=16)
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--ref-sample", type=int, default=8)
+    ap.add_argument("--cpu-threads", type=int, default=32)
     ap.add_argument("--ref-forward", default="cpu", choices=["cpu", "cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

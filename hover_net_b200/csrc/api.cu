@@ -23,6 +23,8 @@ struct hvn_ctx {
     cudaEvent_t tev[2] = {nullptr, nullptr};
     float ms_cnn = 0.f, ms_pp = 0.f;
     long long pp_launches = 0;
+    std::string pp_log;  // per-kernel post-processing times of the last call ("profile" >= 3)
+    std::string log_out;
 };
 
 #define API_BEGIN try {
@@ -116,6 +118,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     std::string k = key ? key : "";
     if (k == "conv_path") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->conv_path = (int)value; }
     else if (k == "chunk") c->chunk = (int)value;
+    else if (k == "branch_streams") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->branch_streams = (int)value; }
     else if (k == "tc_seg_chunks") tc_set_seg_chunks((int)value);
     else if (k == "tc_block_n") tc_set_block_n((int)value);
     else if (k == "profile") { c->profile = (int)value; if (c->model) c->model->profile_ops = value >= 3 ? 2 : (value >= 2 ? 1 : 0); }
@@ -137,7 +140,12 @@ int64_t hvn_get_counter(const hvn_ctx *c, const char *key) {
     return -1;
 }
 
-const char *hvn_debug_log(const hvn_ctx *c) { return (c && c->model) ? c->model->debug_log.c_str() : ""; }
+const char *hvn_debug_log(const hvn_ctx *c) {
+    if (!c) return "";
+    hvn_ctx *m = const_cast<hvn_ctx *>(c);
+    m->log_out = (c->model ? c->model->debug_log : std::string()) + c->pp_log;
+    return m->log_out.c_str();
+}
 
 int hvn_out_shape(const hvn_ctx *c, int in_h, int in_w, int *out_h, int *out_w, int *out_c) {
     API_BEGIN
@@ -163,7 +171,7 @@ static void run_postproc(hvn_ctx *c, const float *pred, int n, int H, int W, int
     HVN_CHECK(nr_types >= 0 && nr_types <= HVN_MAX_TYPES, HVN_ERR_INVALID, "nr_types out of range");
     if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[2], c->stream));
     c->pp_launches += postproc_run(c->pp_arena, c->stream, pred, n, H, W, C, nr_types, inst, (long long *)table,
-                                   max_rows, n_rows);
+                                   max_rows, n_rows, c->profile >= 3 ? &c->pp_log : nullptr);
     if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[3], c->stream));
 }
 static void finish_profile(hvn_ctx *c, bool cnn, bool pp) {

@@ -103,6 +103,9 @@ Model::Model(const std::string &mode_, int nr_types_) : mode(mode_), nr_types(nr
 }
 
 Model::~Model() {
+    for (auto &st : side_) if (st) cudaStreamDestroy(st);
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    for (auto &e : ev_join_) if (e) cudaEventDestroy(e);
     plans_.clear();
     for (void *p : wallocs_) cudaFree(p);
 }
@@ -340,7 +343,8 @@ RawRef rview(const RawRef &b, int y0, int x0, int h, int w, int c0, int c) {
 Plan &Model::plan(int B, int H, int W) {
     HVN_CHECK(finalized, -5, "weights not finalised (call hvn_finalize_weights)");
     HVN_CHECK(H == W, -1, "only square patches are supported (reference patch geometry is square)");
-    std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "p" + std::to_string(conv_path);
+    std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "p" + std::to_string(conv_path) +
+                      "b" + std::to_string(branch_streams);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     std::unique_ptr<Plan> pl(new Plan());
@@ -365,8 +369,10 @@ Plan &Model::plan(int B, int H, int W) {
         r.sN = (long long)h * w * c; r.sH = w * c; r.sW = c; r.h = h; r.w = w; r.c = c;
         return r;
     };
+    int cur_stream = 0;
     auto add_conv = [&](const std::string &wname, const SplitRef &a, int stride, int pad, int ho, int wo) -> Op & {
         Op op;
+        op.stream = cur_stream;
         op.kind = Op::CONV;
         op.name = wname;
         op.cp.a = a;
@@ -384,6 +390,7 @@ Plan &Model::plan(int B, int H, int W) {
     };
     auto add_bnrelu = [&](const std::string &bnp, const RawRef &in, const SplitRef &out) {
         Op op;
+        op.stream = cur_stream;
         op.kind = Op::BNRELU;
         op.name = bnp;
         op.bn_in = in; op.bn_out = out; op.bn = bn_.at(bnp);
@@ -452,10 +459,15 @@ Plan &Model::plan(int B, int H, int W) {
     const int h2 = 2 * w8 - km1, w4 = h2 - 4 * km1;
     const int ho = 2 * w4;
     HVN_CHECK(ho == P.oh, -1, "internal: output size mismatch");
-    RawRef C3 = new_raw(h3, h3, 512), C2 = new_raw(h2, h2, 256);
-    SplitRef T3 = new_split(h3, h3, 512), T2 = new_split(h2, h2, 256);
-    SplitRef B3 = new_split(h3, h3, 128), B2 = new_split(h2, h2, 128);
-    SplitRef U2in = new_split(2 * w8, 2 * w8, 512), U1in = new_split(ho, ho, 256);
+    const int nsets = branch_streams ? (int)branches_.size() : 1;  // private scratch per concurrent branch
+    RawRef C3[3], C2[3];
+    SplitRef T3[3], T2[3], B3[3], B2[3], U2in[3], U1in[3];
+    for (int i = 0; i < nsets; ++i) {
+        C3[i] = new_raw(h3, h3, 512); C2[i] = new_raw(h2, h2, 256);
+        T3[i] = new_split(h3, h3, 512); T2[i] = new_split(h2, h2, 256);
+        B3[i] = new_split(h3, h3, 128); B2[i] = new_split(h2, h2, 128);
+        U2in[i] = new_split(2 * w8, 2 * w8, 512); U1in[i] = new_split(ho, ho, 256);
+    }
     SplitRef Hf[3];
     for (size_t b = 0; b < branches_.size(); ++b) Hf[b] = new_split(ho, ho, 64);
 
@@ -486,9 +498,13 @@ Plan &Model::plan(int B, int H, int W) {
     head.head.B = B; head.head.h = ho; head.head.w_ = ho; head.head.C = P.oc;
     for (size_t b = 0; b < branches_.size(); ++b) {
         const std::string bp = "decoder." + branches_[b] + ".";
-        dense(bp + "u3.", U3in, C3, T3, B3, 2 * ds[3], 256, 8, crop_to(D[1], 2 * w8), U2in);
-        dense(bp + "u2.", U2in, C2, T2, B2, 2 * w8, 128, 4, crop_to(D[0], ho), U1in);
-        { Op &op = add_conv(bp + "u1.conva.weight", U1in, 1, km1 / 2, ho, ho); set_bn(op, bp + "u0.bn", Hf[b]); }
+        const int si_ = branch_streams ? (int)b : 0;
+        cur_stream = si_;
+        const size_t first_op = P.ops.size();
+        dense(bp + "u3.", U3in, C3[si_], T3[si_], B3[si_], 2 * ds[3], 256, 8, crop_to(D[1], 2 * w8), U2in[si_]);
+        dense(bp + "u2.", U2in[si_], C2[si_], T2[si_], B2[si_], 2 * w8, 128, 4, crop_to(D[0], ho), U1in[si_]);
+        { Op &op = add_conv(bp + "u1.conva.weight", U1in[si_], 1, km1 / 2, ho, ho); set_bn(op, bp + "u0.bn", Hf[b]); }
+        if (b == 0) P.ops[first_op].fork_point = true;
         head.head.feat[b] = Hf[b];
         head.head.w[b] = head_w_.at(bp + "u0.conv");
         head.head.bias[b] = head_b_.at(bp + "u0.conv");
@@ -496,6 +512,7 @@ Plan &Model::plan(int B, int H, int W) {
         head.head.kind[b] = branches_[b] == "tp" ? HEAD_TP : (branches_[b] == "np" ? HEAD_NP : HEAD_HV);
         head.flops += 2.0 * B * ho * ho * 64 * head.head.out_ch[b];
     }
+    cur_stream = 0;
     P.ops.push_back(head);
 
     for (auto &op : P.ops) {
@@ -511,7 +528,13 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
     HVN_CHECK(B >= 1, -1, "empty batch");
     int oh, ow, oc;
     out_shape(H, W, oh, ow, oc);
-    if (chunk <= 0) chunk = 8;
+    if (chunk <= 0) chunk = 16;
+    if (!side_[0]) {
+        for (auto &st : side_) HVN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        HVN_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+        for (auto &e : ev_join_) HVN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t main_stream = s;
     struct Rec { const char *cls; double flops; cudaEvent_t a, b; const Op *op; };
     std::vector<Rec> recs;
     if (profile_ops) { class_ms.clear(); class_flops.clear(); class_launches.clear(); }
@@ -521,7 +544,24 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
         int bc = std::min(chunk, B - b0);
         Plan &P = plan(bc, H, W);
         last_flops += P.flops;
+        int prev_stream = 0;
+        bool forked[3] = {true, false, false};
         for (auto &op : P.ops) {
+            // fork: a side stream starts after everything issued so far on the context stream;
+            // join: the context stream waits for the side streams before the op that follows them
+            if (op.fork_point && branch_streams) {
+                HVN_CUDA(cudaEventRecord(ev_fork_, main_stream));
+                for (int i = 1; i < 3; ++i) { HVN_CUDA(cudaStreamWaitEvent(side_[i - 1], ev_fork_, 0)); forked[i] = true; }
+            }
+            if (op.stream == 0 && prev_stream != 0) {
+                for (int i = 1; i < 3; ++i)
+                    if (forked[i]) {
+                        HVN_CUDA(cudaEventRecord(ev_join_[i - 1], side_[i - 1]));
+                        HVN_CUDA(cudaStreamWaitEvent(main_stream, ev_join_[i - 1], 0));
+                    }
+            }
+            prev_stream = op.stream;
+            s = op.stream == 0 ? main_stream : side_[op.stream - 1];
             Rec r{nullptr, op.flops, nullptr, nullptr, &op};
             if (profile_ops) {
                 HVN_CUDA(cudaEventCreate(&r.a));
@@ -555,6 +595,7 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
             if (profile_ops) { HVN_CUDA(cudaEventRecord(r.b, s)); recs.push_back(r); }
         }
     }
+    s = main_stream;
     HVN_CUDA(cudaGetLastError());
     if (profile_ops) {
         HVN_CUDA(cudaStreamSynchronize(s));

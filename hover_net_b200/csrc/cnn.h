@@ -37,6 +37,8 @@ struct Op {
     // HEAD
     HeadParams head;
     double flops = 0;       // 2*MACs of the reference layer (algorithmic)
+    int stream = 0;         // 0 = context stream; 1,2 = side streams (decoder branches run concurrently)
+    bool fork_point = false; // side streams may start once everything before this op has been issued
 };
 
 struct Plan {
@@ -59,6 +61,7 @@ class Model {
     std::map<std::string, int> index;
     std::map<std::string, std::vector<float>> host;
     bool finalized = false;
+    int branch_streams = 1;  // run the decoder branches on separate streams
     int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only, 2 auto + per-layer self test
 
     void load(const std::string &name, const float *data, int ndim, const int64_t *shape);
@@ -86,6 +89,8 @@ class Model {
     std::vector<void *> wallocs_;
     std::map<std::string, std::unique_ptr<Plan>> plans_;
     std::vector<std::string> branches_;
+    cudaStream_t side_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork_ = nullptr, ev_join_[2] = {nullptr, nullptr};
     void add_spec(const std::string &name, std::initializer_list<int64_t> shape, bool ignored = false);
     void add_bn(const std::string &prefix, int c);
     const std::vector<float> &hostp(const std::string &name) const;

@@ -293,13 +293,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         make_float4(acc[c0 + 4 * g], acc[c0 + 4 * g + 1], acc[c0 + 4 * g + 2], acc[c0 + 4 * g + 3]);
                 __syncwarp();
                 const int ch = tn * BLOCK_N + cb + c0 + sub_g * 4;
+                constexpr int PB = MODE == EPI_UP2 ? 4 : 8;  // pixels-per-lane whose loads are in flight together
 #pragma unroll
-                for (int bt = 0; bt < 2; ++bt) {
-                    int pv[4], pn[4], py[4], px[4];
-                    EpiPre<MODE> pre[4];
+                for (int bt = 0; bt < 8 / PB; ++bt) {
+                    int pv[PB], pn[PB], py[PB], px[PB];
+                    EpiPre<MODE> pre[PB];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int src = (bt * 4 + u) * 4 + sub_px;
+                    for (int u = 0; u < PB; ++u) {
+                        const int src = (bt * PB + u) * 4 + sub_px;
                         pv[u] = __shfl_sync(0xffffffffu, (int)valid, src);
                         pn[u] = __shfl_sync(0xffffffffu, n_img, src);
                         py[u] = __shfl_sync(0xffffffffu, oy, src);
@@ -307,8 +308,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         if (pv[u]) epi_prefetch<MODE>(P, pn[u], py[u], px[u], ch, pre[u]);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int src = (bt * 4 + u) * 4 + sub_px;
+                    for (int u = 0; u < PB; ++u) {
+                        const int src = (bt * PB + u) * 4 + sub_px;
                         const float4 t = *reinterpret_cast<const float4 *>(&ep_tile[src * 32 + ((sub_g ^ (src & 7)) << 2)]);
                         if (pv[u]) {
                             float v[4] = {t.x, t.y, t.z, t.w};

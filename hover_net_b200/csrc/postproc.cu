@@ -20,6 +20,10 @@
 #include "common.cuh"
 #include "postproc.h"
 
+#include <string>
+#include <utility>
+#include <vector>
+
 namespace hvn {
 
 // ------------------------------------------------------------------------------------------------
@@ -450,6 +454,37 @@ __global__ void k_marker_labels(int N, const int *__restrict__ Lall, const int *
     }
 }
 
+// A blob that holds exactly one marker label is flooded entirely by that label whatever the order
+// (the blob is 4-connected), and a blob without markers stays 0: only blobs with >= 2 distinct labels
+// need the ordered flood below.  lab_range[k] = (min,max) marker label inside blob k.
+__global__ void k_blob_marker_range(int N, const int *__restrict__ inst_all, const int *__restrict__ L1_all,
+                                    const int *__restrict__ blob_of_root_all, int2 *__restrict__ range_all, int max_blobs) {
+    int m = blockIdx.y;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        int lab = inst_all[(size_t)m * N + p];
+        if (lab <= 0) continue;
+        int k = blob_of_root_all[(size_t)m * N + L1_all[(size_t)m * N + p]];
+        int *r = (int *)&range_all[(size_t)m * max_blobs + k];
+        atomicMin(r, lab);
+        atomicMax(r + 1, lab);
+    }
+}
+__global__ void k_blob_fill_single(int N, int *__restrict__ inst_all, const unsigned char *__restrict__ fg_all,
+                                   const int *__restrict__ L1_all, const int *__restrict__ blob_of_root_all,
+                                   const int2 *__restrict__ range_all, int max_blobs) {
+    int m = blockIdx.y;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        if (!fg_all[(size_t)m * N + p]) continue;
+        int k = blob_of_root_all[(size_t)m * N + L1_all[(size_t)m * N + p]];
+        int2 r = range_all[(size_t)m * max_blobs + k];
+        if (r.y > 0 && r.x == r.y) inst_all[(size_t)m * N + p] = r.y;
+    }
+}
+__global__ void k_range_init(int2 *r, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = make_int2(0x7fffffff, 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // :88 skimage.segmentation.watershed(dist, markers, mask=blb)  (0.17.2; connectivity 1, no
 // compactness, no watershed line): a priority flood ordered by (value, age) with the label written
@@ -510,7 +545,8 @@ struct Heap4 {
 __global__ void __launch_bounds__(32)
 k_watershed(int H, int W, const double *__restrict__ dist_all, const unsigned char *__restrict__ fg_all,
             const int *__restrict__ L1_all, const int *__restrict__ size1_all,
-            const int *__restrict__ blob_root_all, const int4 *__restrict__ bbox_all, int max_blobs,
+            const int *__restrict__ blob_root_all, const int4 *__restrict__ bbox_all,
+            const int2 *__restrict__ range_all, int max_blobs,
             HeapItem *__restrict__ heap_all, int *inst_all, PPStats *st) {
     extern __shared__ __align__(16) unsigned char ws_smem[];
     int m = blockIdx.y, N = H * W;
@@ -518,6 +554,7 @@ k_watershed(int H, int W, const double *__restrict__ dist_all, const unsigned ch
     int nb = st[m].nblobs;
     if (nb > max_blobs) nb = max_blobs;
     if (k >= nb) return;
+    { int2 rg = range_all[(size_t)m * max_blobs + k]; if (rg.y == 0 || rg.x == rg.y) return; }
     const int lane = threadIdx.x;
     const double *dist = dist_all + (size_t)m * N;
     const unsigned char *fg = fg_all + (size_t)m * N;
@@ -587,38 +624,52 @@ k_watershed(int H, int W, const double *__restrict__ dist_all, const unsigned ch
 // map from a shared queue (large blobs first).  Same flood, same order -- only the memory it lives in
 // differs from k_watershed, which remains the path for maps too large for shared memory.
 constexpr int WT_WARPS = 8;
-template <typename StateT>
-struct HeapS {  // like Heap4 but with a runtime shared-memory capacity
-    HeapItem *s, *g;
+constexpr int WT_BIG = 2048;     // blobs >= this many px are flooded by warp 0 with the large heap
+constexpr int WT_SMALL_CAP = 512;
+
+// Compact heap entry for maps with < 65536 px: fp32 rounding of the priority + (age << 16 | idx).
+// float(x) is monotone in x, so k differs => the fp64 order is decided; on equal k the exact fp64
+// values are fetched and compared, then the age -- the same strict order as (value, age) in fp64.
+struct HeapC { float k; unsigned int meta; };
+
+struct HeapT {
+    HeapC *s, *g;
+    const double *dist;
     int n, cap;
-    __device__ __forceinline__ HeapItem get(int i) const { return i < cap ? s[i] : g[i - cap]; }
-    __device__ __forceinline__ void set(int i, const HeapItem &e) { if (i < cap) s[i] = e; else g[i - cap] = e; }
-    __device__ __forceinline__ void push(const HeapItem &e) {
+    __device__ __forceinline__ bool smaller(const HeapC &a, const HeapC &b) const {
+        if (a.k != b.k) return a.k < b.k;
+        const double da = dist[a.meta & 0xffffu], db = dist[b.meta & 0xffffu];
+        if (da != db) return da < db;
+        return (a.meta >> 16) < (b.meta >> 16);
+    }
+    __device__ __forceinline__ HeapC get(int i) const { return i < cap ? s[i] : g[i - cap]; }
+    __device__ __forceinline__ void set(int i, const HeapC &e) { if (i < cap) s[i] = e; else g[i - cap] = e; }
+    __device__ __forceinline__ void push(const HeapC &e) {
         int i = n++;
         while (i > 0) {
             int p = (i - 1) >> 2;
-            HeapItem pe = get(p);
-            if (!h_smaller(e, pe)) break;
+            HeapC pe = get(p);
+            if (!smaller(e, pe)) break;
             set(i, pe);
             i = p;
         }
         set(i, e);
     }
-    __device__ __forceinline__ HeapItem pop() {
-        HeapItem top = get(0);
-        HeapItem last = get(--n);
+    __device__ __forceinline__ HeapC pop() {
+        HeapC top = get(0);
+        HeapC last = get(--n);
         int i = 0;
         while (true) {
             int c = 4 * i + 1;
             if (c >= n) break;
-            HeapItem best = get(c);
+            HeapC best = get(c);
             int bi = c;
             int ce = min(c + 4, n);
             for (int j = c + 1; j < ce; ++j) {
-                HeapItem e = get(j);
-                if (h_smaller(e, best)) { best = e; bi = j; }
+                HeapC e = get(j);
+                if (smaller(e, best)) { best = e; bi = j; }
             }
-            if (!h_smaller(best, last)) break;
+            if (!smaller(best, last)) break;
             set(i, best);
             i = bi;
         }
@@ -628,18 +679,19 @@ struct HeapS {  // like Heap4 but with a runtime shared-memory capacity
 };
 
 __global__ void __launch_bounds__(WT_WARPS * 32)
-k_watershed_tile(int H, int W, int heap_cap, const double *__restrict__ dist_all,
+k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
                  const unsigned char *__restrict__ fg_all, const int *__restrict__ L1_all,
                  const int *__restrict__ size1_all, const int *__restrict__ blob_root_all,
-                 const int4 *__restrict__ bbox_all, int max_blobs, HeapItem *__restrict__ heap_all,
-                 int *__restrict__ inst_all, PPStats *st) {
+                 const int4 *__restrict__ bbox_all, const int2 *__restrict__ range_all, int max_blobs,
+                 HeapItem *__restrict__ heap_all, int *__restrict__ inst_all, PPStats *st) {
     extern __shared__ __align__(16) unsigned char wt_smem[];
     __shared__ int s_next[2];
+    const unsigned int wmagic = (unsigned int)((0x100000000ull + (unsigned)W - 1) / (unsigned)W);  // idx / W for idx < 2^16
     const int m = blockIdx.x, N = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     short *state = reinterpret_cast<short *>(wt_smem);
     const size_t state_bytes = ((size_t)N * 2 + 15) & ~(size_t)15;
-    HeapItem *heaps = reinterpret_cast<HeapItem *>(wt_smem + state_bytes);
+    HeapC *heaps = reinterpret_cast<HeapC *>(wt_smem + state_bytes);
     const double *dist = dist_all + (size_t)m * N;
     const unsigned char *fg = fg_all + (size_t)m * N;
     const int *L1 = L1_all + (size_t)m * N;
@@ -649,71 +701,73 @@ k_watershed_tile(int H, int W, int heap_cap, const double *__restrict__ dist_all
     __syncthreads();
     int nb = st[m].nblobs;
     if (nb > max_blobs) nb = max_blobs;
-    HeapS<short> hp;
-    hp.s = heaps + (size_t)warp * heap_cap;
-    hp.cap = heap_cap;
-    for (int pass = 0; pass < 2; ++pass) {  // pass 0: blobs >= 512 px (long floods start first), pass 1: the rest
-        while (true) {
-            int k = 0;
-            if (lane == 0) k = atomicAdd(&s_next[pass], 1);
-            k = __shfl_sync(0xffffffffu, k, 0);
-            if (k >= nb) break;
-            const int root = blob_root_all[(size_t)m * max_blobs + k];
-            const int bsize = size1_all[(size_t)m * N + root];
-            if ((bsize >= 512) != (pass == 0)) continue;
-            const int4 bb = bbox_all[(size_t)m * max_blobs + k];
-            int goff = 0;
-            if (lane == 0) goff = atomicAdd(&st[m].heap_top, bsize);
-            goff = __shfl_sync(0xffffffffu, goff, 0);
-            hp.g = heap_all + (size_t)m * N + goff;
-            hp.n = 0;
-            const int bw = bb.w - bb.y + 1, bh = bb.z - bb.x + 1, area = bw * bh;
-            for (int base = 0; base < area; base += 32) {
-                int i = base + lane;
-                bool is = false;
-                int p = 0;
-                double dv = 0.0;
-                if (i < area) {
-                    int yy = bb.x + i / bw, xx = bb.y + i % bw;
-                    p = yy * W + xx;
-                    is = state[p] > 0 && L1[p] == root;
-                    if (is) dv = dist[p];
-                }
-                unsigned int msk = __ballot_sync(0xffffffffu, is);
-                while (msk) {
-                    int src = __ffs(msk) - 1;
-                    msk &= msk - 1;
-                    int pp = __shfl_sync(0xffffffffu, p, src);
-                    double dd = __shfl_sync(0xffffffffu, dv, src);
-                    if (lane == 0) { HeapItem e; e.v = dd; e.age = 0; e.idx = pp; hp.push(e); }
-                }
+    HeapT hp;
+    hp.dist = dist;
+    // warp 0: large blobs, one after the other, with the large heap; warps 1..7: the small ones
+    const int pass = warp == 0 ? 0 : 1;
+    hp.s = warp == 0 ? heaps : heaps + big_cap + (size_t)(warp - 1) * WT_SMALL_CAP;
+    hp.cap = warp == 0 ? big_cap : WT_SMALL_CAP;
+    while (true) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&s_next[pass], 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nb) break;
+        const int root = blob_root_all[(size_t)m * max_blobs + k];
+        const int bsize = size1_all[(size_t)m * N + root];
+        if ((bsize >= WT_BIG) != (pass == 0)) continue;
+        { const int2 rg = range_all[(size_t)m * max_blobs + k]; if (rg.y == 0 || rg.x == rg.y) continue; }
+        const int4 bb = bbox_all[(size_t)m * max_blobs + k];
+        int goff = 0;
+        if (lane == 0) goff = atomicAdd(&st[m].heap_top, bsize);
+        goff = __shfl_sync(0xffffffffu, goff, 0);
+        hp.g = reinterpret_cast<HeapC *>(heap_all + (size_t)m * N + goff);  // 16 B/px arena >= 8 B/entry
+        hp.n = 0;
+        const int bw = bb.w - bb.y + 1, bh = bb.z - bb.x + 1, area = bw * bh;
+        for (int base = 0; base < area; base += 32) {
+            int i = base + lane;
+            bool is = false;
+            int p = 0;
+            float kv = 0.f;
+            if (i < area) {
+                int yy = bb.x + i / bw, xx = bb.y + i % bw;
+                p = yy * W + xx;
+                is = state[p] > 0 && L1[p] == root;
+                if (is) kv = (float)dist[p];
             }
-            if (lane == 0) {
-                int age = 1;
-                while (hp.n > 0) {
-                    HeapItem e = hp.pop();
-                    const int y = e.idx / W, x = e.idx - y * W;
-                    const short lab = state[e.idx];
-                    int q[4] = {y > 0 ? e.idx - W : -1, x > 0 ? e.idx - 1 : -1, x < W - 1 ? e.idx + 1 : -1,
-                                y < H - 1 ? e.idx + W : -1};
-                    bool take[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) take[j] = q[j] >= 0 && state[q[j]] == 0;
-                    double dv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dv[j] = take[j] ? __ldg(dist + q[j]) : 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (take[j]) {
-                            age += 1;
-                            state[q[j]] = lab;
-                            HeapItem ne; ne.v = dv[j]; ne.age = age; ne.idx = q[j];
-                            hp.push(ne);
-                        }
-                }
+            unsigned int msk = __ballot_sync(0xffffffffu, is);
+            while (msk) {
+                int src = __ffs(msk) - 1;
+                msk &= msk - 1;
+                int pp = __shfl_sync(0xffffffffu, p, src);
+                float kk = __shfl_sync(0xffffffffu, kv, src);
+                if (lane == 0) { HeapC e; e.k = kk; e.meta = (unsigned int)pp; hp.push(e); }  // age 0
             }
-            __syncwarp();
         }
+        if (lane == 0) {
+            unsigned int age = 1;
+            while (hp.n > 0) {
+                HeapC e = hp.pop();
+                const int idx = (int)(e.meta & 0xffffu);
+                const int y = (int)__umulhi((unsigned int)idx, wmagic), x = idx - y * W;
+                const short lab = state[idx];
+                int q[4] = {y > 0 ? idx - W : -1, x > 0 ? idx - 1 : -1, x < W - 1 ? idx + 1 : -1, y < H - 1 ? idx + W : -1};
+                bool take[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) take[j] = q[j] >= 0 && state[q[j]] == 0;
+                double dv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dv[j] = take[j] ? __ldg(dist + q[j]) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (take[j]) {
+                        age += 1;
+                        state[q[j]] = lab;
+                        HeapC ne; ne.k = (float)dv[j]; ne.meta = (age << 16) | (unsigned int)q[j];
+                        hp.push(ne);
+                    }
+            }
+        }
+        __syncwarp();
     }
     __syncthreads();
     for (int p = threadIdx.x; p < N; p += blockDim.x) { short v = state[p]; inst[p] = v > 0 ? (int)v : 0; }
@@ -815,6 +869,7 @@ static void pp_layout(A &ar, PostprocBuffers &b, int n, int H, int W, int nr_typ
     b.blob_of_root = ar.template take<int>(T);
     b.blob_root = ar.template take<int>((size_t)n * b.max_blobs);
     b.bbox = ar.template take<int4>((size_t)n * b.max_blobs);
+    b.lab_range = ar.template take<int2>((size_t)n * b.max_blobs);
     b.sobh = ar.template take<double>(T);
     b.sobv = ar.template take<double>(T);
     b.din = ar.template take<double>(T);
@@ -842,7 +897,7 @@ size_t postproc_workspace_bytes(int n, int H, int W, int nr_types) {
 
 // Runs the whole post-processing path for n maps on `stream`.  Returns the number of kernel launches.
 int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, int H, int W, int C, int nr_types,
-                 int *inst, long long *table, int max_rows, int *n_rows) {
+                 int *inst, long long *table, int max_rows, int *n_rows, std::string *prof) {
     HVN_CHECK(C == 3 || C == 4, -1, "postproc: C must be 3 (np,hv_x,hv_y) or 4 (tp,np,hv_x,hv_y)");
     HVN_CHECK(C == 4 || nr_types == 0, -1, "postproc: nr_types given but the map has no type channel");
     HVN_CHECK(H >= 1 && W >= 1 && n >= 1, -1, "postproc: empty input");
@@ -857,13 +912,23 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
     int launches = 0;
     const int TPB = 256;
     dim3 g1((unsigned)min(cdiv(N, TPB), 1024), (unsigned)n);
-#define L(...) do { __VA_ARGS__; ++launches; } while (0)
+    std::vector<std::pair<const char *, cudaEvent_t>> evs;
+    auto mark = [&](const char *name) {
+        if (!prof) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream);
+        evs.emplace_back(name, e);
+    };
+    mark("start");
+#define L(...) do { __VA_ARGS__; ++launches; mark(#__VA_ARGS__); } while (0)
     L(k_init_stats<<<cdiv(n, 128), 128, 0, stream>>>((PPStats *)b.stats, n));
     HVN_CUDA(cudaMemsetAsync(b.size1, 0, T * sizeof(int), stream));
     HVN_CUDA(cudaMemsetAsync(b.size3, 0, T * sizeof(int), stream));
     HVN_CUDA(cudaMemsetAsync(b.flag, 0, T, stream));
     HVN_CUDA(cudaMemsetAsync(b.tcnt, 0, (size_t)n * b.max_ids * (nr_types > 0 ? nr_types : 1) * sizeof(int), stream));
     L(k_bbox_init<<<cdiv((size_t)n * b.max_blobs, TPB), TPB, 0, stream>>>((int4 *)b.bbox, (size_t)n * b.max_blobs));
+    L(k_range_init<<<cdiv((size_t)n * b.max_blobs, TPB), TPB, 0, stream>>>((int2 *)b.lab_range, (size_t)n * b.max_blobs));
     L(k_acc_init<<<cdiv((size_t)n * b.max_ids, TPB), TPB, 0, stream>>>((InstAcc *)b.acc, (size_t)n * b.max_ids));
     PPStats *st = (PPStats *)b.stats;
     // foreground
@@ -894,23 +959,27 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
     L(k_assign_ids<<<gr, TPB, 0, stream>>>(H, W, b.L2, b.rowcnt, b.id3));
     L(k_marker_labels<<<g1, TPB, 0, stream>>>(N, b.L2, b.size3, b.id3, b.fg, inst));
     // flood
+    L(k_blob_marker_range<<<g1, TPB, 0, stream>>>(N, inst, b.L1, b.blob_of_root, (int2 *)b.lab_range, b.max_blobs));
+    L(k_blob_fill_single<<<g1, TPB, 0, stream>>>(N, inst, b.fg, b.L1, b.blob_of_root, (int2 *)b.lab_range, b.max_blobs));
     {
         // patch-sized maps: per-map CTA with the flood state in shared memory; otherwise the generic kernel
-        const size_t budget = 200 * 1024, state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15);
-        long long cap = state_bytes < budget ? (long long)((budget - state_bytes) / (WT_WARPS * sizeof(HeapItem))) : 0;
-        if (cap > 4096) cap = 4096;
-        if (cap >= 256 && b.max_ids < 32000) {
+        const size_t budget = 208 * 1024, state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15);
+        const size_t small_bytes = (size_t)(WT_WARPS - 1) * WT_SMALL_CAP * sizeof(HeapC);
+        long long cap = state_bytes + small_bytes < budget ? (long long)((budget - state_bytes - small_bytes) / sizeof(HeapC)) : 0;
+        if (cap > 16384) cap = 16384;
+        if (cap >= 1024 && N < 65536 && b.max_ids < 32000) {
             static bool attr = false;
             if (!attr) {
                 HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 1024));
                 attr = true;
             }
-            size_t smem = state_bytes + (size_t)cap * WT_WARPS * sizeof(HeapItem);
+            size_t smem = state_bytes + small_bytes + (size_t)cap * sizeof(HeapC);
             L(k_watershed_tile<<<n, WT_WARPS * 32, smem, stream>>>(H, W, (int)cap, b.dist, b.fg, b.L1, b.size1, b.blob_root,
-                                                             (int4 *)b.bbox, b.max_blobs, (HeapItem *)b.heap, inst, st));
+                                                             (int4 *)b.bbox, (const int2 *)b.lab_range, b.max_blobs, (HeapItem *)b.heap, inst, st));
         } else {
             L(k_watershed<<<dim3((unsigned)b.max_blobs, (unsigned)n), 32, WS_CAP * sizeof(HeapItem), stream>>>(
-                H, W, b.dist, b.fg, b.L1, b.size1, b.blob_root, (int4 *)b.bbox, b.max_blobs, (HeapItem *)b.heap, inst, st));
+                H, W, b.dist, b.fg, b.L1, b.size1, b.blob_root, (int4 *)b.bbox, (const int2 *)b.lab_range, b.max_blobs,
+                (HeapItem *)b.heap, inst, st));
         }
     }
     // table
@@ -918,6 +987,20 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
     L(k_table_rows<<<n, 1024, 0, stream>>>((InstAcc *)b.acc, b.tcnt, nr_types, b.max_ids, table, max_rows, n_rows, st));
 #undef L
     HVN_CUDA(cudaGetLastError());
+    if (prof) {
+        HVN_CUDA(cudaStreamSynchronize(stream));
+        prof->clear();
+        for (size_t i = 1; i < evs.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i - 1].second, evs[i].second);
+            std::string nm(evs[i].first);
+            nm = nm.substr(0, nm.find("<<<"));
+            char line[160];
+            snprintf(line, sizeof(line), "pp %-28s %9.4f ms\n", nm.c_str(), ms);
+            *prof += line;
+        }
+        for (auto &e : evs) cudaEventDestroy(e.second);
+    }
     return launches;
 }
 

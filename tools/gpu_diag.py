@@ -130,3 +130,49 @@ def cpuf():
 
 if __name__ == "__main__" and "cpuf" in sys.argv[1:]:
     cpuf()
+
+
+def ppprof(B=64):
+    """per-kernel post-processing time on CNN-output maps and on synthetic nuclei maps"""
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    net = create_model(mode="fast", nr_types=6)
+    net.load_state_dict(synth.make_state_dict("fast", 6, 0))
+    x = synth.make_patches(8, 256, seed=1)
+    x = np.concatenate([x] * (B // 8))
+    pred = net.ctx.forward(x)
+    fg = (pred[..., 1] >= 0.5)
+    print("CNN-output maps: fg fraction %.3f" % fg.mean())
+    net.ctx.set_option("profile", 3)
+    for name, maps in (("cnn-output", pred), ("synthetic nuclei", np.stack([synth.synth_pred_map(164, 164, 6, s) for s in range(B)]))):
+        net.ctx.postproc(maps, 6); net.ctx.postproc(maps, 6)
+        print("== %s: total %.3f ms for %d maps" % (name, net.ctx.stage_ms("postproc"), B))
+        rows = [l for l in net.ctx.debug_log().split("\n") if l.startswith("pp ")]
+        rows.sort(key=lambda l: -float(l.split()[-2]))
+        print("\n".join(rows[:8]))
+    net.ctx.close()
+
+
+if __name__ == "__main__" and "ppprof" in sys.argv[1:]:
+    ppprof()
+
+
+def sweep():
+    """CNN-only device time vs chunk size and branch streams (B=64, fast)"""
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    net = create_model(mode="fast", nr_types=6)
+    net.load_state_dict(synth.make_state_dict("fast", 6, 0))
+    x = np.concatenate([synth.make_patches(8, 256, seed=1)] * 8)
+    net.ctx.set_option("profile", 1)
+    ref = None
+    for bs in (0, 1):
+        for chunk in (8, 16, 32):
+            net.ctx.set_option("branch_streams", bs); net.ctx.set_option("chunk", chunk)
+            out = net.ctx.forward(x); out = net.ctx.forward(x)
+            if ref is None: ref = out
+            print("branch_streams=%d chunk=%2d: cnn %.2f ms for 64 patches (%.3f ms/patch) same=%s" % (
+                bs, chunk, net.ctx.stage_ms("cnn"), net.ctx.stage_ms("cnn") / 64, np.array_equal(out, ref)))
+    net.ctx.close()
+
+
+if __name__ == "__main__" and "sweep" in sys.argv[1:]:
+    sweep()
