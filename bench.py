@@ -179,6 +179,7 @@ def run_ours(args):
     rank, world, local = dist_env()
     import torch
     from hover_net_b200 import _lib, synth
+    from hover_net_b200.dist import gather_tables
     from hover_net_b200.models.hovernet.net_desc import create_model
 
     if world > 1:
@@ -207,8 +208,7 @@ def run_ours(args):
     d_tab = torch.zeros((B, max_rows, 10), dtype=torch.int64, device="cuda")
     d_nr = torch.zeros((B,), dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    g_tab = torch.zeros((world * B, max_rows, 10), dtype=torch.int64, device="cuda") if world > 1 else None
-    g_nr = torch.zeros((world * B,), dtype=torch.int32, device="cuda") if world > 1 else None
+    gathered = [None, None]
     torch.cuda.synchronize()
 
     def step_resident():
@@ -218,8 +218,7 @@ def run_ours(args):
     def gather():
         if world > 1:
             ctx.sync()
-            dist.all_gather_into_tensor(g_nr, d_nr)
-            dist.all_gather_into_tensor(g_tab, d_tab)
+            gathered[0], gathered[1] = gather_tables(d_tab, d_nr)
 
     def barrier():
         ctx.sync()

@@ -624,60 +624,86 @@ k_watershed(int H, int W, const double *__restrict__ dist_all, const unsigned ch
 // map from a shared queue (large blobs first).  Same flood, same order -- only the memory it lives in
 // differs from k_watershed, which remains the path for maps too large for shared memory.
 constexpr int WT_WARPS = 8;
-constexpr int WT_BIG = 2048;     // blobs >= this many px are flooded by warp 0 with the large heap
-constexpr int WT_SMALL_CAP = 512;
+constexpr int WT_BIG = 2048;      // blobs >= this many px are flooded by warp 0 with the large heap
+constexpr int WT_SMALL_CAP = 256; // shared-memory heap entries of warps 1..7 (the rest spills to global)
 
-// Compact heap entry for maps with < 65536 px: fp32 rounding of the priority + (age << 16 | idx).
-// float(x) is monotone in x, so k differs => the fp64 order is decided; on equal k the exact fp64
-// values are fetched and compared, then the age -- the same strict order as (value, age) in fp64.
-struct HeapC { float k; unsigned int meta; };
-
-struct HeapT {
-    HeapC *s, *g;
+// Heap entry for maps with < 65536 px, one 64-bit word: [ fkey(float(priority)) | age:16 | idx:16 ].
+// float() is monotone, so when the high words differ the u64 order IS the (fp64 value, age) order; when
+// they are equal the exact fp64 priorities are fetched and compared, then (age, idx).  Entries of one
+// blob therefore pop in exactly the order of skimage's (value, age) heap (equal-valued age-0 marker
+// pixels excepted).  1-based 4-ary heap: children of i are 4i-2..4i+1 (one aligned 32-byte
+// group), parent of j is (j+2)>>2; slots past the end hold ~0 so a full group can be read blindly.
+typedef unsigned long long u64;
+struct HeapQ {
+    u64 *s;              // shared part, slots [1, cap]
+    u64 *g;              // global spill, slots (cap, ...)
     const double *dist;
     int n, cap;
-    __device__ __forceinline__ bool smaller(const HeapC &a, const HeapC &b) const {
-        if (a.k != b.k) return a.k < b.k;
-        const double da = dist[a.meta & 0xffffu], db = dist[b.meta & 0xffffu];
+    __device__ __forceinline__ bool less_exact(u64 a, u64 b) const {
+        const double da = dist[(unsigned int)a & 0xffffu], db = dist[(unsigned int)b & 0xffffu];
         if (da != db) return da < db;
-        return (a.meta >> 16) < (b.meta >> 16);
+        return (unsigned int)a < (unsigned int)b;
     }
-    __device__ __forceinline__ HeapC get(int i) const { return i < cap ? s[i] : g[i - cap]; }
-    __device__ __forceinline__ void set(int i, const HeapC &e) { if (i < cap) s[i] = e; else g[i - cap] = e; }
-    __device__ __forceinline__ void push(const HeapC &e) {
-        int i = n++;
-        while (i > 0) {
-            int p = (i - 1) >> 2;
-            HeapC pe = get(p);
-            if (!smaller(e, pe)) break;
-            set(i, pe);
-            i = p;
+    __device__ __forceinline__ bool less(u64 a, u64 b) const {
+        if ((a >> 32) != (b >> 32)) return a < b;
+        return less_exact(a, b);
+    }
+    __device__ __forceinline__ u64 get(int i) const { return i <= cap ? s[i] : g[i - cap]; }
+    __device__ __forceinline__ void set(int i, u64 e) { if (i <= cap) s[i] = e; else g[i - cap] = e; }
+    __device__ __forceinline__ void push(u64 e) {
+        int j = ++n;
+        while (j > 1) {
+            const int p = (j + 2) >> 2;
+            const u64 pe = get(p);
+            if (!less(e, pe)) break;
+            set(j, pe);
+            j = p;
         }
-        set(i, e);
+        set(j, e);
     }
-    __device__ __forceinline__ HeapC pop() {
-        HeapC top = get(0);
-        HeapC last = get(--n);
-        int i = 0;
+    __device__ __forceinline__ u64 pop() {
+        const u64 top = get(1);
+        const u64 last = get(n);
+        set(n, ~0ull);
+        --n;
+        if (n == 0) return top;
+        int i = 1;
         while (true) {
-            int c = 4 * i + 1;
-            if (c >= n) break;
-            HeapC best = get(c);
-            int bi = c;
-            int ce = min(c + 4, n);
-            for (int j = c + 1; j < ce; ++j) {
-                HeapC e = get(j);
-                if (smaller(e, best)) { best = e; bi = j; }
+            const int c = 4 * i - 2;
+            if (c > n) break;
+            u64 best;
+            int bi;
+            if (c + 3 <= cap) {  // whole child group in shared memory (slots past n read as ~0)
+                const ulonglong2 q0 = *reinterpret_cast<const ulonglong2 *>(s + c);
+                const ulonglong2 q1 = *reinterpret_cast<const ulonglong2 *>(s + c + 2);
+                u64 m0 = q0.x < q0.y ? q0.x : q0.y, m1 = q1.x < q1.y ? q1.x : q1.y;
+                int i0 = q0.x < q0.y ? c : c + 1, i1 = q1.x < q1.y ? c + 2 : c + 3;
+                best = m0 < m1 ? m0 : m1;
+                bi = m0 < m1 ? i0 : i1;
+                const unsigned int kb = (unsigned int)(best >> 32);
+                const int same = ((unsigned int)(q0.x >> 32) == kb) + ((unsigned int)(q0.y >> 32) == kb) +
+                                 ((unsigned int)(q1.x >> 32) == kb) + ((unsigned int)(q1.y >> 32) == kb);
+                if (same > 1 && kb != 0xffffffffu) {  // fp32 tie among the children: decide exactly
+                    best = q0.x; bi = c;
+                    if (c + 1 <= n && less(q0.y, best)) { best = q0.y; bi = c + 1; }
+                    if (c + 2 <= n && less(q1.x, best)) { best = q1.x; bi = c + 2; }
+                    if (c + 3 <= n && less(q1.y, best)) { best = q1.y; bi = c + 3; }
+                }
+            } else {
+                best = get(c); bi = c;
+                const int ce = min(c + 3, n);
+                for (int j = c + 1; j <= ce; ++j) { const u64 e = get(j); if (less(e, best)) { best = e; bi = j; } }
             }
-            if (!smaller(best, last)) break;
+            if (!less(best, last)) break;
             set(i, best);
             i = bi;
         }
-        if (n > 0) set(i, last);
+        set(i, last);
         return top;
     }
 };
 
+template <bool KK>
 __global__ void __launch_bounds__(WT_WARPS * 32)
 k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
                  const unsigned char *__restrict__ fg_all, const int *__restrict__ L1_all,
@@ -689,23 +715,30 @@ k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
     const unsigned int wmagic = (unsigned int)((0x100000000ull + (unsigned)W - 1) / (unsigned)W);  // idx / W for idx < 2^16
     const int m = blockIdx.x, N = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    short *state = reinterpret_cast<short *>(wt_smem);
-    const size_t state_bytes = ((size_t)N * 2 + 15) & ~(size_t)15;
-    HeapC *heaps = reinterpret_cast<HeapC *>(wt_smem + state_bytes);
+    // layout: heaps (u64, 16-byte aligned groups) | kk (float per px, optional) | state (int16 per px)
+    u64 *heaps = reinterpret_cast<u64 *>(wt_smem);
+    const size_t heap_slots = (size_t)(big_cap + 4) + (size_t)(WT_WARPS - 1) * (WT_SMALL_CAP + 4);
+    float *kk = reinterpret_cast<float *>(wt_smem + heap_slots * 8);
+    short *state = reinterpret_cast<short *>(wt_smem + heap_slots * 8 + (KK ? (((size_t)N * 4 + 15) & ~(size_t)15) : 0));
     const double *dist = dist_all + (size_t)m * N;
     const unsigned char *fg = fg_all + (size_t)m * N;
     const int *L1 = L1_all + (size_t)m * N;
     int *inst = inst_all + (size_t)m * N;
-    for (int p = threadIdx.x; p < N; p += blockDim.x) state[p] = fg[p] ? (short)inst[p] : (short)-1;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        state[p] = fg[p] ? (short)inst[p] : (short)-1;
+        if (KK) kk[p] = (float)dist[p] + 0.0f;  // +0.0f: -0.0 and +0.0 are equal priorities, give them one key
+    }
+    for (size_t i = threadIdx.x; i < heap_slots; i += blockDim.x) heaps[i] = ~0ull;
     if (threadIdx.x < 2) s_next[threadIdx.x] = 0;
     __syncthreads();
     int nb = st[m].nblobs;
     if (nb > max_blobs) nb = max_blobs;
-    HeapT hp;
+    HeapQ hp;
     hp.dist = dist;
-    // warp 0: large blobs, one after the other, with the large heap; warps 1..7: the small ones
+    // warp 0: large blobs, one after the other, with the large heap; warps 1..7: the small ones.
+    // Each heap region starts 2 slots in, so that slot index c = 4i-2 is 16-byte aligned.
     const int pass = warp == 0 ? 0 : 1;
-    hp.s = warp == 0 ? heaps : heaps + big_cap + (size_t)(warp - 1) * WT_SMALL_CAP;
+    hp.s = (warp == 0 ? heaps : heaps + (big_cap + 4) + (size_t)(warp - 1) * (WT_SMALL_CAP + 4));
     hp.cap = warp == 0 ? big_cap : WT_SMALL_CAP;
     while (true) {
         int k = 0;
@@ -720,50 +753,49 @@ k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
         int goff = 0;
         if (lane == 0) goff = atomicAdd(&st[m].heap_top, bsize);
         goff = __shfl_sync(0xffffffffu, goff, 0);
-        hp.g = reinterpret_cast<HeapC *>(heap_all + (size_t)m * N + goff);  // 16 B/px arena >= 8 B/entry
+        hp.g = reinterpret_cast<u64 *>(heap_all + (size_t)m * N + goff);  // 16 B/px arena >= 8 B/entry
         hp.n = 0;
         const int bw = bb.w - bb.y + 1, bh = bb.z - bb.x + 1, area = bw * bh;
         for (int base = 0; base < area; base += 32) {
             int i = base + lane;
             bool is = false;
             int p = 0;
-            float kv = 0.f;
+            unsigned int kv = 0;
             if (i < area) {
                 int yy = bb.x + i / bw, xx = bb.y + i % bw;
                 p = yy * W + xx;
                 is = state[p] > 0 && L1[p] == root;
-                if (is) kv = (float)dist[p];
+                if (is) kv = fkey(KK ? kk[p] : (float)dist[p] + 0.0f);
             }
             unsigned int msk = __ballot_sync(0xffffffffu, is);
             while (msk) {
                 int src = __ffs(msk) - 1;
                 msk &= msk - 1;
                 int pp = __shfl_sync(0xffffffffu, p, src);
-                float kk = __shfl_sync(0xffffffffu, kv, src);
-                if (lane == 0) { HeapC e; e.k = kk; e.meta = (unsigned int)pp; hp.push(e); }  // age 0
+                unsigned int kq = __shfl_sync(0xffffffffu, kv, src);
+                if (lane == 0) hp.push(((u64)kq << 32) | (u64)(unsigned int)pp);  // age 0
             }
         }
         if (lane == 0) {
             unsigned int age = 1;
             while (hp.n > 0) {
-                HeapC e = hp.pop();
-                const int idx = (int)(e.meta & 0xffffu);
+                const u64 e = hp.pop();
+                const int idx = (int)((unsigned int)e & 0xffffu);
                 const int y = (int)__umulhi((unsigned int)idx, wmagic), x = idx - y * W;
                 const short lab = state[idx];
-                int q[4] = {y > 0 ? idx - W : -1, x > 0 ? idx - 1 : -1, x < W - 1 ? idx + 1 : -1, y < H - 1 ? idx + W : -1};
+                const int q[4] = {y > 0 ? idx - W : -1, x > 0 ? idx - 1 : -1, x < W - 1 ? idx + 1 : -1, y < H - 1 ? idx + W : -1};
                 bool take[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) take[j] = q[j] >= 0 && state[q[j]] == 0;
-                double dv[4];
+                unsigned int kq[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dv[j] = take[j] ? __ldg(dist + q[j]) : 0.0;
+                for (int j = 0; j < 4; ++j) kq[j] = take[j] ? fkey(KK ? kk[q[j]] : (float)__ldg(dist + q[j]) + 0.0f) : 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (take[j]) {
                         age += 1;
                         state[q[j]] = lab;
-                        HeapC ne; ne.k = (float)dv[j]; ne.meta = (age << 16) | (unsigned int)q[j];
-                        hp.push(ne);
+                        hp.push(((u64)kq[j] << 32) | (u64)((age << 16) | (unsigned int)q[j]));
                     }
             }
         }
@@ -963,19 +995,27 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
     L(k_blob_fill_single<<<g1, TPB, 0, stream>>>(N, inst, b.fg, b.L1, b.blob_of_root, (int2 *)b.lab_range, b.max_blobs));
     {
         // patch-sized maps: per-map CTA with the flood state in shared memory; otherwise the generic kernel
-        const size_t budget = 208 * 1024, state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15);
-        const size_t small_bytes = (size_t)(WT_WARPS - 1) * WT_SMALL_CAP * sizeof(HeapC);
-        long long cap = state_bytes + small_bytes < budget ? (long long)((budget - state_bytes - small_bytes) / sizeof(HeapC)) : 0;
-        if (cap > 16384) cap = 16384;
+        const size_t budget = 225 * 1024;
+        const size_t state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15), kk_bytes = (((size_t)N * 4 + 15) & ~(size_t)15);
+        const size_t small_bytes = (size_t)(WT_WARPS - 1) * (WT_SMALL_CAP + 4) * 8;
+        const bool use_kk = state_bytes + kk_bytes + small_bytes + (2048 + 4) * 8 <= budget;
+        const size_t fixed = state_bytes + (use_kk ? kk_bytes : 0) + small_bytes;
+        long long cap = fixed + 64 < budget ? (long long)((budget - fixed) / 8) - 4 : 0;
+        cap = std::min<long long>(cap & ~3ll, 16384);
         if (cap >= 1024 && N < 65536 && b.max_ids < 32000) {
             static bool attr = false;
             if (!attr) {
-                HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 1024));
+                HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
+                HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
                 attr = true;
             }
-            size_t smem = state_bytes + small_bytes + (size_t)cap * sizeof(HeapC);
-            L(k_watershed_tile<<<n, WT_WARPS * 32, smem, stream>>>(H, W, (int)cap, b.dist, b.fg, b.L1, b.size1, b.blob_root,
-                                                             (int4 *)b.bbox, (const int2 *)b.lab_range, b.max_blobs, (HeapItem *)b.heap, inst, st));
+            size_t smem = fixed + (size_t)(cap + 4) * 8;
+            if (use_kk)
+                L(k_watershed_tile<true><<<n, WT_WARPS * 32, smem, stream>>>(H, W, (int)cap, b.dist, b.fg, b.L1, b.size1, b.blob_root,
+                    (int4 *)b.bbox, (const int2 *)b.lab_range, b.max_blobs, (HeapItem *)b.heap, inst, st));
+            else
+                L(k_watershed_tile<false><<<n, WT_WARPS * 32, smem, stream>>>(H, W, (int)cap, b.dist, b.fg, b.L1, b.size1, b.blob_root,
+                    (int4 *)b.bbox, (const int2 *)b.lab_range, b.max_blobs, (HeapItem *)b.heap, inst, st));
         } else {
             L(k_watershed<<<dim3((unsigned)b.max_blobs, (unsigned)n), 32, WS_CAP * sizeof(HeapItem), stream>>>(
                 H, W, b.dist, b.fg, b.L1, b.size1, b.blob_root, (int4 *)b.bbox, (const int2 *)b.lab_range, b.max_blobs,
