@@ -259,6 +259,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 oy = ty * G.bh + py; ox = tx * G.bw + px;
                 valid = row < G.bw * G.bh && oy < P.ho && ox < P.wo;
             }
+            // The transposed write-out below maps lane -> (pixel sub_px + 4*it, channel group sub_g).  In
+            // residual mode the whole tile's residual values are requested now, before the accumulator is
+            // waited for, so their HBM latency hides behind the main loop.
+            const int sub_px = lane >> 3, sub_g = lane & 7;
+            constexpr int NCH = CW / 32;
+            float4 rpre[MODE == EPI_RES ? NCH : 1][MODE == EPI_RES ? 8 : 1];
+            if constexpr (MODE == EPI_RES) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int src = it * 4 + sub_px;
+                    const int pv = __shfl_sync(0xffffffffu, (int)valid, src);
+                    const int pn = __shfl_sync(0xffffffffu, n_img, src);
+                    const int py = __shfl_sync(0xffffffffu, oy, src);
+                    const int px = __shfl_sync(0xffffffffu, ox, src);
+#pragma unroll
+                    for (int cc = 0; cc < NCH; ++cc) {
+                        rpre[cc][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pv)
+                            rpre[cc][it] = *reinterpret_cast<const float4 *>(
+                                P.res.p + pn * P.res.sN + (long long)py * P.res.sH + (long long)px * P.res.sW +
+                                tn * BLOCK_N + cb + cc * 32 + sub_g * 4);
+                    }
+                }
+            }
             float acc[CW];
 #pragma unroll
             for (int j = 0; j < CW; ++j) acc[j] = 0.f;
@@ -283,8 +307,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             // would scatter 8-byte pieces over 32 cache lines per instruction.  Each warp passes 32px x 32ch
             // blocks through its private (XOR-swizzled) shared-memory tile so that 8 lanes cover the 32
             // channels of one pixel: 128 B of fp32 / 64 B of fp16 contiguous per pixel per instruction.
-            // Residual / skip loads of 4 pixels-per-lane are issued before any of them is consumed.
-            const int sub_px = lane >> 3, sub_g = lane & 7;
+            // Skip loads (upsample mode) of 4 pixels-per-lane are issued before any of them is consumed.
 #pragma unroll
             for (int c0 = 0; c0 < CW; c0 += 32) {
 #pragma unroll
@@ -305,7 +328,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         pn[u] = __shfl_sync(0xffffffffu, n_img, src);
                         py[u] = __shfl_sync(0xffffffffu, oy, src);
                         px[u] = __shfl_sync(0xffffffffu, ox, src);
-                        if (pv[u]) epi_prefetch<MODE>(P, pn[u], py[u], px[u], ch, pre[u]);
+                        if constexpr (MODE == EPI_RES) pre[u].r = rpre[c0 / 32][bt * PB + u];
+                        else if (pv[u]) epi_prefetch<MODE>(P, pn[u], py[u], px[u], ch, pre[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < PB; ++u) {
