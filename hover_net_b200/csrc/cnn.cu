@@ -297,6 +297,10 @@ void Model::selftest_conv(const Op &op, cudaStream_t s) {
     const bool trace = getenv("HVN_TRACE") != nullptr;
     if (trace) { fprintf(stderr, "[selftest] %s ...\n", op.name.c_str()); fflush(stderr); }
     tc_launch(a, op.tc, s);
+    if (b.in_scale) {  // referee path of a transformed-input layer: BN+ReLU pass into the scratch view, then the conv
+        launch_bnrelu(b.a_raw, B, b.in_scale, b.in_shift, b.a, s);
+        b.in_scale = b.in_shift = nullptr;
+    }
     launch_conv_ref(b, s);
     if (op.cp.out_raw.p) {
         const RawRef &r = op.cp.out_raw;
@@ -344,7 +348,7 @@ Plan &Model::plan(int B, int H, int W) {
     HVN_CHECK(finalized, -5, "weights not finalised (call hvn_finalize_weights)");
     HVN_CHECK(H == W, -1, "only square patches are supported (reference patch geometry is square)");
     std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "p" + std::to_string(conv_path) +
-                      "b" + std::to_string(branch_streams);
+                      "b" + std::to_string(branch_streams) + "x" + std::to_string(xform);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     std::unique_ptr<Plan> pl(new Plan());
@@ -401,6 +405,7 @@ Plan &Model::plan(int B, int H, int W) {
         return pad / 2;
     };
 
+    const bool use_xf = xform && conv_path != 1;
     // ---- stem
     const int s0 = mode == "fast" ? H : H - 6;
     SplitRef X0 = new_split(s0, s0, 64);
@@ -429,14 +434,23 @@ Plan &Model::plan(int B, int H, int W) {
             SplitRef a1 = A1;  // unit 0 runs conv1 at the group's input resolution; later units reuse the
                                // same allocation as a compact [ri,ri,c1] tensor
             if (ri != A1.h) { a1.h = ri; a1.w = ri; a1.sH = ri * g.c1; a1.sN = (long long)ri * ri * g.c1; }
-            { Op &op = add_conv(p + "conv1.weight", in, 1, 0, ri, ri); set_bn(op, p + "conv1/bn", a1); }
+            {
+                Op &op = add_conv(p + "conv1.weight", in, 1, 0, ri, ri);
+                set_bn(op, p + "conv1/bn", a1);
+                if (u != 0 && use_xf) {  // A = relu(bn_preact(S)) formed in the kernel from the raw running sum
+                    const BNParams &pb = bn_.at(p + "preact/bn");
+                    op.cp.a_raw = S; op.cp.in_scale = pb.scale; op.cp.in_shift = pb.shift;
+                }
+            }
             int lo = tf_same_lo(ri, 3, st);
             { Op &op = add_conv(p + "conv2.weight", a1, st, lo, so, so); set_bn(op, p + "conv2/bn", A2); }
             {
                 Op &op = add_conv(p + "conv3.weight", A2, 1, 0, so, so);
                 op.cp.res = S;
-                if (u + 1 < g.units) { op.cp.out_raw = S; set_bn(op, gn + ".units." + std::to_string(u + 1) + ".preact/bn", Pp); }
-                else set_bn(op, gn + ".blk_bna.bn", Pp);
+                if (u + 1 < g.units) {
+                    op.cp.out_raw = S;
+                    if (!use_xf) set_bn(op, gn + ".units." + std::to_string(u + 1) + ".preact/bn", Pp);
+                } else set_bn(op, gn + ".blk_bna.bn", Pp);
             }
         }
         x = Pp; D[gi] = Pp; ds[gi] = so; si = so;
@@ -479,17 +493,25 @@ Plan &Model::plan(int B, int H, int W) {
         for (int i = 0; i < units; ++i) {
             int wi = hh - i * km1, oi = i * km1 / 2, wn = wi - km1, on = oi + km1 / 2;
             std::string q = pfx + "dense.units." + std::to_string(i) + ".";
-            add_bnrelu(q + "preact_bna/bn", rview(Cb, oi, oi, wi, wi, 0, c), sview(Tb, oi, oi, wi, wi, 0, c));
+            if (!use_xf) add_bnrelu(q + "preact_bna/bn", rview(Cb, oi, oi, wi, wi, 0, c), sview(Tb, oi, oi, wi, wi, 0, c));
             { Op &op = add_conv(q + "conv1.weight", sview(Tb, oi, oi, wi, wi, 0, c), 1, 0, wi, wi);
-              set_bn(op, q + "conv1/bn", sview(Bb, oi, oi, wi, wi, 0, 128)); }
+              set_bn(op, q + "conv1/bn", sview(Bb, oi, oi, wi, wi, 0, 128));
+              if (use_xf) {
+                  const BNParams &pb = bn_.at(q + "preact_bna/bn");
+                  op.cp.a_raw = rview(Cb, oi, oi, wi, wi, 0, c); op.cp.in_scale = pb.scale; op.cp.in_shift = pb.shift;
+              } }
             { Op &op = add_conv(q + "conv2.weight", sview(Bb, oi, oi, wi, wi, 0, 128), 1, 0, wn, wn);
               op.cp.out_raw = rview(Cb, on, on, wn, wn, c, 32); }
             c += 32;
         }
         int wl = hh - units * km1, ol = units * km1 / 2;
-        add_bnrelu(pfx + "dense.blk_bna.bn", rview(Cb, ol, ol, wl, wl, 0, c), sview(Tb, ol, ol, wl, wl, 0, c));
+        if (!use_xf) add_bnrelu(pfx + "dense.blk_bna.bn", rview(Cb, ol, ol, wl, wl, 0, c), sview(Tb, ol, ol, wl, wl, 0, c));
         Op &op = add_conv(pfx + "convf.weight", sview(Tb, ol, ol, wl, wl, 0, c), 1, 0, wl, wl);
         op.cp.up2 = 1; op.cp.skip = skip; op.cp.out_split = out;
+        if (use_xf) {
+            const BNParams &pb = bn_.at(pfx + "dense.blk_bna.bn");
+            op.cp.a_raw = rview(Cb, ol, ol, wl, wl, 0, c); op.cp.in_scale = pb.scale; op.cp.in_shift = pb.shift;
+        }
     };
 
     Op head;
@@ -577,7 +599,15 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
             case Op::CONV:
                 if (op.tc.ok && conv_path == 2) selftest_conv(op, s);
                 if (op.tc.ok) { tc_launch(op.cp, op.tc, s); ++tc_launches; r.cls = "conv_tc"; }
-                else { launch_conv_ref(op.cp, s); r.cls = "conv_ref"; }
+                else {
+                    ConvParams q = op.cp;
+                    if (q.in_scale) {  // materialise the pre-activated operand for the referee kernel
+                        launch_bnrelu(q.a_raw, bc, q.in_scale, q.in_shift, q.a, s);
+                        q.in_scale = q.in_shift = nullptr;
+                    }
+                    launch_conv_ref(q, s);
+                    r.cls = "conv_ref";
+                }
                 break;
             case Op::BNRELU:
                 launch_bnrelu(op.bn_in, bc, op.bn.scale, op.bn.shift, op.bn_out, s);

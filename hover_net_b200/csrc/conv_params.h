@@ -28,6 +28,11 @@ struct ConvWeights {         // [tap][cout][cin_pad] fp16 hi/lo, K-major per tap
 
 struct ConvParams {
     SplitRef a;              // input view (bounds of the view are the zero-padding bounds)
+    // Optional transformed input (1x1 stride-1 layers): A = split(relu(a_raw * in_scale + in_shift)) is
+    // formed on the fly by the kernel's transform warps from the raw fp32 tensor, instead of being read
+    // from a pre-transformed split tensor.  `a` must then describe the same view (used by the referee).
+    RawRef a_raw;
+    const float *in_scale = nullptr, *in_shift = nullptr;
     ConvWeights w;
     int stride = 1, pad_t = 0, pad_l = 0;
     int B = 0, ho = 0, wo = 0;

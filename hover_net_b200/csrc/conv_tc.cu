@@ -20,6 +20,10 @@
 //   relative at K=9216).  The K loop is therefore cut into segments of SEG_CHUNKS 64-channel slices
 //   (96 MMAs); each segment accumulates in its own TMEM buffer and the epilogue warps drain it into
 //   fp32 registers (round-to-nearest adds) while the next segment runs in the other buffer.
+// * XF variant (1x1 layers fed by a raw fp32 tensor through a pre-activation BatchNorm+ReLU): four
+//   extra "transform" warps build the A tiles themselves -- coalesced fp32 loads, y=relu(x*scale+shift),
+//   fp16 hi/lo split, 128B-swizzled st.shared, fence.proxy.async -- so the pre-activated copy of the
+//   tensor never exists in HBM (no separate BN/ReLU pass, no second output of the producing layer).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -108,13 +112,14 @@ struct TcGeom {
 };
 
 constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int XF_WARPS = 4;              // XF variant: warps 10..13 transform the A operand
 constexpr int EP_WARPS = 8;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 
 template <int BLOCK_N> __host__ __device__ constexpr int tc_stage_bytes() { return 2 * A_TILE_BYTES + 2 * BLOCK_N * 128; }
 
-template <int BLOCK_N, int STAGES, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BLOCK_N, int STAGES, int MODE, bool XF>
+__global__ void __launch_bounds__(TC_THREADS + (XF ? XF_WARPS * 32 : 0), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
           const ConvParams P, const TcGeom G) {
@@ -135,7 +140,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -151,7 +156,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     const int total_tiles = G.tiles_m * G.tiles_n;
     const int taps = P.w.taps;
     const int kiters = taps * G.kchunks;
-    const uint32_t tx_bytes = (uint32_t)(2 * (G.flat ? 128 : G.bw * G.bh) * 128 + 2 * BLOCK_N * 128);
+    const uint32_t tx_bytes = (uint32_t)((XF ? 0 : 2 * (G.flat ? 128 : G.bw * G.bh) * 128) + 2 * BLOCK_N * 128);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -178,7 +183,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                                    b_lo = b_hi + BLOCK_N * 128;
                     mbar_expect_tx(full_bar(s), tx_bytes);
                     const int tap = it / G.kchunks, kc = it - tap * G.kchunks;
-                    if (G.flat) {
+                    if constexpr (XF) {
+                        // A tiles are written by the transform warps
+                    } else if (G.flat) {
                         tma_2d(a_hi, &tm_a_hi, full_bar(s), kc * 64, (int)m0);
                         tma_2d(a_lo, &tm_a_lo, full_bar(s), kc * 64, (int)m0);
                     } else {
@@ -226,6 +233,83 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     }
                     tc_commit(tfull_bar(as));     // segment complete -> epilogue warps drain it
                 }
+            }
+        }
+    } else if (XF && warp >= 2 + EP_WARPS) {
+        // ===================== A-operand transform (warps 10..13, XF only) =====================
+        // thread -> (row group rg = t>>4, float4 column l16 = t&15): one warp instruction reads 2 rows x 256 B
+        const int t = threadIdx.x - (2 + EP_WARPS) * 32;
+        const int l16 = t & 15, rg = t >> 4;
+        const int wl = t & 31;
+        uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+        int it_global = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int tm = tile / G.tiles_n;
+            // element offsets of this thread's 16 rows (rows rg + 8*i), -1 = row outside the tensor
+            int roff[16];
+            {
+                int n_img = 0, y0 = 0, x0 = 0;
+                if (!G.flat) {
+                    const int per_img = G.tiles_x * G.tiles_y;
+                    n_img = tm / per_img;
+                    const int r = tm - n_img * per_img;
+                    y0 = (r / G.tiles_x) * G.bh;
+                    x0 = (r - (r / G.tiles_x) * G.tiles_x) * G.bw;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int row = rg + 8 * i;
+                    int n, y, x;
+                    bool ok;
+                    if (G.flat) {
+                        const long long m = (long long)tm * 128 + row;
+                        ok = m < G.m_total;
+                        const long long hw = (long long)P.ho * P.wo;
+                        n = ok ? (int)(m / hw) : 0;
+                        const int r2 = ok ? (int)(m - (long long)n * hw) : 0;
+                        y = r2 / P.wo; x = r2 - y * P.wo;
+                    } else {
+                        const int py = row / G.bw, px = row - py * G.bw;
+                        n = n_img; y = y0 + py; x = x0 + px;
+                        ok = row < G.bw * G.bh && y < P.a_raw.h && x < P.a_raw.w;
+                    }
+                    roff[i] = ok ? (int)(n * P.a_raw.sN + (long long)y * P.a_raw.sH + (long long)x * P.a_raw.sW) : -1;
+                }
+            }
+            for (int kc = 0; kc < kiters; ++kc, ++it_global) {  // taps == 1: kiters == kchunks
+                const int s = it_global % STAGES;
+                const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
+                const int c = kc * 64 + l16 * 4;
+                const bool cok = c < P.w.cin;
+                float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+                if (cok) {
+                    sc = *reinterpret_cast<const float4 *>(P.in_scale + c);
+                    sh = *reinterpret_cast<const float4 *>(P.in_shift + c);
+                }
+                float4 v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cok && roff[i] >= 0) v[i] = *reinterpret_cast<const float4 *>(P.a_raw.p + roff[i] + c);
+                }
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int row = rg + 8 * i;
+                    const float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
+                                         fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
+                    __half oh[4], ol[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) split_f32(y4[k], oh[k], ol[k]);
+                    // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+                    const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
+                    *reinterpret_cast<uint2 *>(a_hi + off) = *reinterpret_cast<uint2 *>(oh);
+                    *reinterpret_cast<uint2 *>(a_lo + off) = *reinterpret_cast<uint2 *>(ol);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (wl == 0) mbar_arrive(full_bar(s));
             }
         }
     } else {
@@ -397,21 +481,33 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     if (w.cin_pad % 64 != 0 || w.cout % 32 != 0) return false;
     if (P.stride != 1 && P.stride != 2) return false;
     if (P.pad_t != P.pad_l) return false;
-    if ((reinterpret_cast<uintptr_t>(P.a.hi) & 15) || (reinterpret_cast<uintptr_t>(P.a.lo) & 15)) return false;
-    if ((P.a.sW % 8) || (P.a.sH % 8) || (P.a.sN % 8)) return false;
+    const bool xf = P.in_scale != nullptr;
+    if (xf) {
+        if (w.taps != 1 || P.stride != 1 || P.pad_t != 0 || P.res.p) return false;
+        if ((reinterpret_cast<uintptr_t>(P.a_raw.p) & 15) || (P.a_raw.sW % 4) || (P.a_raw.sH % 4) || (P.a_raw.sN % 4)) return false;
+        if ((long long)P.B * P.a_raw.sN >= (1ll << 31)) return false;  // 32-bit element offsets in the transform warps
+    } else {
+        if ((reinterpret_cast<uintptr_t>(P.a.hi) & 15) || (reinterpret_cast<uintptr_t>(P.a.lo) & 15)) return false;
+        if ((P.a.sW % 8) || (P.a.sH % 8) || (P.a.sN % 8)) return false;
+    }
     int bn = w.cout >= 128 ? 128 : (w.cout >= 64 ? 64 : 32);
     if (g_force_block_n && w.cout % g_force_block_n == 0) bn = g_force_block_n;
     if (w.cout % bn) return false;
     plan.block_n = bn;
-    const bool dense_rows = (long long)P.a.sW * P.a.w == P.a.sH && (long long)P.a.sH * P.a.h == P.a.sN;
-    plan.flat = (w.taps == 1 && P.stride == 1 && P.pad_t == 0 && dense_rows && P.ho == P.a.h && P.wo == P.a.w) ? 1 : 0;
+    const bool dense_rows = xf ? ((long long)P.a_raw.sW * P.a_raw.w == P.a_raw.sH && (long long)P.a_raw.sH * P.a_raw.h == P.a_raw.sN)
+                               : ((long long)P.a.sW * P.a.w == P.a.sH && (long long)P.a.sH * P.a.h == P.a.sN);
+    const int ah = xf ? P.a_raw.h : P.a.h, aw = xf ? P.a_raw.w : P.a.w;
+    plan.flat = (w.taps == 1 && P.stride == 1 && P.pad_t == 0 && dense_rows && P.ho == ah && P.wo == aw) ? 1 : 0;
+    if (xf && bn != 128 && bn != 64) return false;
     cuuint32_t ones[4] = {1, 1, 1, 1};
     if (plan.flat) {
         cuuint64_t dims[2] = {(cuuint64_t)P.a.c, (cuuint64_t)((long long)P.B * P.a.h * P.a.w)};
         cuuint64_t str[1] = {(cuuint64_t)P.a.sW * 2};
         cuuint32_t box[2] = {64, 128};
-        if (!encode(plan.tmap_a_hi, P.a.hi, 2, dims, str, box, ones)) return false;
-        if (!encode(plan.tmap_a_lo, P.a.lo, 2, dims, str, box, ones)) return false;
+        if (!xf) {
+            if (!encode(plan.tmap_a_hi, P.a.hi, 2, dims, str, box, ones)) return false;
+            if (!encode(plan.tmap_a_lo, P.a.lo, 2, dims, str, box, ones)) return false;
+        }
         plan.bw = 128; plan.bh = 1; plan.tiles_x = plan.tiles_y = 0;
     } else {
         // choose the (bw x bh <= 128) pixel rectangle that wastes the fewest accumulator rows
@@ -432,8 +528,10 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
         cuuint64_t str[3] = {(cuuint64_t)P.a.sW * 2, (cuuint64_t)P.a.sH * 2, (cuuint64_t)P.a.sN * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)(plan.bw * P.stride), (cuuint32_t)(plan.bh * P.stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)P.stride, (cuuint32_t)P.stride, 1};
-        if (!encode(plan.tmap_a_hi, P.a.hi, 4, dims, str, box, estr)) return false;
-        if (!encode(plan.tmap_a_lo, P.a.lo, 4, dims, str, box, estr)) return false;
+        if (!xf) {
+            if (!encode(plan.tmap_a_hi, P.a.hi, 4, dims, str, box, estr)) return false;
+            if (!encode(plan.tmap_a_lo, P.a.lo, 4, dims, str, box, estr)) return false;
+        }
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout, (cuuint64_t)w.taps};
@@ -446,13 +544,13 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     return true;
 }
 
-template <int BLOCK_N, int STAGES, int MODE>
+template <int BLOCK_N, int STAGES, int MODE, bool XF>
 static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 16 + EP_WARPS * 32 * 32 * 4 + 1024;
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr = false;
     if (!attr) {
-        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES, MODE, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     static int sms = 0;
@@ -465,14 +563,22 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
     CUtensorMap a_hi, a_lo, w_hi, w_lo;
     memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
     memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
-    k_conv_tc<BLOCK_N, STAGES, MODE><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
+    k_conv_tc<BLOCK_N, STAGES, MODE, XF><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
 }
 
 template <int BLOCK_N, int STAGES>
 static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
-    if (P.up2) launch_tm<BLOCK_N, STAGES, EPI_UP2>(P, plan, G, s);
-    else if (P.res.p) launch_tm<BLOCK_N, STAGES, EPI_RES>(P, plan, G, s);
-    else launch_tm<BLOCK_N, STAGES, EPI_PLAIN>(P, plan, G, s);
+    if (P.in_scale) {  // transformed input: only the shapes the plan produces (1x1, plain or upsample epilogue)
+        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {
+            if (P.up2) launch_tm<BLOCK_N, STAGES, EPI_UP2, true>(P, plan, G, s);
+            else launch_tm<BLOCK_N, STAGES, EPI_PLAIN, true>(P, plan, G, s);
+            return;
+        }
+        throw Error(-1, "conv_tc: transformed input with unsupported tile shape");
+    }
+    if (P.up2) launch_tm<BLOCK_N, STAGES, EPI_UP2, false>(P, plan, G, s);
+    else if (P.res.p) launch_tm<BLOCK_N, STAGES, EPI_RES, false>(P, plan, G, s);
+    else launch_tm<BLOCK_N, STAGES, EPI_PLAIN, false>(P, plan, G, s);
 }
 
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {

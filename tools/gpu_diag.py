@@ -58,7 +58,7 @@ def tc(mode="fast", nt=6, verbose=False):
     x = synth.make_patches(int(g["batch"]), arch.PATCH_GEOMETRY[mode][0], seed=7)
     net = create_model(mode=mode, nr_types=nt)
     net.load_state_dict(synth.make_state_dict(mode, nt, 0))
-    for seg in (8, 4, 16):
+    for seg in (4,):
         net.ctx.set_option("tc_seg_chunks", seg)
         net.ctx.set_option("conv_path", 2)
         out = net.ctx.forward(x)
@@ -99,6 +99,7 @@ def layers(mode="fast", B=8):
     net = create_model(mode=mode, nr_types=nt)
     net.load_state_dict(synth.make_state_dict(mode, nt, 0))
     net.ctx.set_option("chunk", B)
+    net.ctx.set_option("branch_streams", 0)
     net.ctx.forward(x)
     net.ctx.set_option("profile", 3)
     net.ctx.forward(x)
