@@ -133,7 +133,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-    const uint32_t ep_base = bar_base + 8u * (2 * STAGES + 4) + 16u;  // 8 warps x [32][32] fp32 transpose tiles (XOR-swizzled)
+    // XF only: raw_full[2], raw_empty[2] barriers and a 2-slot ring of raw fp32 [128][64] staging tiles
+    auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * r; };
+    auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * (2 + r); };
+    const uint32_t ep_base = bar_base + 8u * (2 * STAGES + 4) + 48u;  // 8 warps x [32][32] fp32 transpose tiles (XOR-swizzled)
+    const uint32_t raw_base = (ep_base + EP_WARPS * 4096u + 1023u) & ~1023u;
+    constexpr uint32_t RAW_TILE_BYTES = 128 * 64 * 4;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,6 +147,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
+        if (XF) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), XF_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -175,6 +181,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     x0 = (r - (r / G.tiles_x) * G.tiles_x) * G.bw;
                 }
                 for (int it = 0; it < kiters; ++it, ++it_global) {
+                    if constexpr (XF) {  // raw fp32 A tile of this K-slice -> staging ring (tm_a_hi is the fp32 map)
+                        const int r = it_global & 1;
+                        const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
+                        mbar_wait(rempty_bar(r), rph ^ 1u);
+                        mbar_expect_tx(rfull_bar(r), (uint32_t)((G.flat ? 128 : G.bw * G.bh) * 256));
+                        if (G.flat) tma_2d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), it * 64, (int)m0);
+                        else tma_4d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), it * 64, x0, y0, n_img);
+                    }
                     const int s = it_global % STAGES;
                     const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
@@ -237,48 +251,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         }
     } else if (XF && warp >= 2 + EP_WARPS) {
         // ===================== A-operand transform (warps 10..13, XF only) =====================
-        // thread -> (row group rg = t>>4, float4 column l16 = t&15): one warp instruction reads 2 rows x 256 B
+        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + 8*i: raw fp32 staging tile
+        // (row-major [128][64], filled by TMA) -> y = relu(x*scale+shift) -> fp16 hi/lo -> swizzled A tiles
         const int t = threadIdx.x - (2 + EP_WARPS) * 32;
         const int l16 = t & 15, rg = t >> 4;
         const int wl = t & 31;
         uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+        const uint8_t *raw_gen = smem_raw + (raw_base - smem_u32(smem_raw));
         int it_global = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int tm = tile / G.tiles_n;
-            // element offsets of this thread's 16 rows (rows rg + 8*i), -1 = row outside the tensor
-            int roff[16];
-            {
-                int n_img = 0, y0 = 0, x0 = 0;
-                if (!G.flat) {
-                    const int per_img = G.tiles_x * G.tiles_y;
-                    n_img = tm / per_img;
-                    const int r = tm - n_img * per_img;
-                    y0 = (r / G.tiles_x) * G.bh;
-                    x0 = (r - (r / G.tiles_x) * G.tiles_x) * G.bw;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int row = rg + 8 * i;
-                    int n, y, x;
-                    bool ok;
-                    if (G.flat) {
-                        const long long m = (long long)tm * 128 + row;
-                        ok = m < G.m_total;
-                        const long long hw = (long long)P.ho * P.wo;
-                        n = ok ? (int)(m / hw) : 0;
-                        const int r2 = ok ? (int)(m - (long long)n * hw) : 0;
-                        y = r2 / P.wo; x = r2 - y * P.wo;
-                    } else {
-                        const int py = row / G.bw, px = row - py * G.bw;
-                        n = n_img; y = y0 + py; x = x0 + px;
-                        ok = row < G.bw * G.bh && y < P.a_raw.h && x < P.a_raw.w;
-                    }
-                    roff[i] = ok ? (int)(n * P.a_raw.sN + (long long)y * P.a_raw.sH + (long long)x * P.a_raw.sW) : -1;
-                }
-            }
             for (int kc = 0; kc < kiters; ++kc, ++it_global) {  // taps == 1: kiters == kchunks
                 const int s = it_global % STAGES;
                 const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
+                const int r = it_global & 1;
+                const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
                 const int c = kc * 64 + l16 * 4;
                 const bool cok = c < P.w.cin;
                 float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
@@ -286,19 +272,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     sc = *reinterpret_cast<const float4 *>(P.in_scale + c);
                     sh = *reinterpret_cast<const float4 *>(P.in_shift + c);
                 }
-                float4 v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (cok && roff[i] >= 0) v[i] = *reinterpret_cast<const float4 *>(P.a_raw.p + roff[i] + c);
-                }
+                mbar_wait(rfull_bar(r), rph);
                 mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint8_t *src = raw_gen + r * RAW_TILE_BYTES;
                 uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
+#pragma unroll 4
                 for (int i = 0; i < 16; ++i) {
                     const int row = rg + 8 * i;
-                    const float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
-                                         fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
+                    const float4 v = *reinterpret_cast<const float4 *>(src + row * 256 + l16 * 16);
+                    float y4[4] = {fmaxf(v.x * sc.x + sh.x, 0.f), fmaxf(v.y * sc.y + sh.y, 0.f),
+                                   fmaxf(v.z * sc.z + sh.z, 0.f), fmaxf(v.w * sc.w + sh.w, 0.f)};
+                    if (!cok) y4[0] = y4[1] = y4[2] = y4[3] = 0.f;  // channels past cin (zero weights) must stay finite
                     __half oh[4], ol[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) split_f32(y4[k], oh[k], ol[k]);
@@ -309,7 +293,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (wl == 0) mbar_arrive(full_bar(s));
+                if (wl == 0) { mbar_arrive(full_bar(s)); mbar_arrive(rempty_bar(r)); }
             }
         }
     } else {
@@ -458,12 +442,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-                   const cuuint32_t *box, const cuuint32_t *estr) {
+                   const cuuint32_t *box, const cuuint32_t *estr, bool raw_f32 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     alignas(64) CUtensorMap tm;
-    CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = fn(&tm, raw_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base,
+                    dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    raw_f32 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     memcpy(dst, &tm, sizeof(tm));
@@ -507,6 +492,10 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
         if (!xf) {
             if (!encode(plan.tmap_a_hi, P.a.hi, 2, dims, str, box, ones)) return false;
             if (!encode(plan.tmap_a_lo, P.a.lo, 2, dims, str, box, ones)) return false;
+        } else {
+            cuuint64_t rdims[2] = {(cuuint64_t)P.a_raw.c, (cuuint64_t)((long long)P.B * P.a_raw.h * P.a_raw.w)};
+            cuuint64_t rstr[1] = {(cuuint64_t)P.a_raw.sW * 4};
+            if (!encode(plan.tmap_a_hi, P.a_raw.p, 2, rdims, rstr, box, ones, true)) return false;
         }
         plan.bw = 128; plan.bh = 1; plan.tiles_x = plan.tiles_y = 0;
     } else {
@@ -531,6 +520,10 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
         if (!xf) {
             if (!encode(plan.tmap_a_hi, P.a.hi, 4, dims, str, box, estr)) return false;
             if (!encode(plan.tmap_a_lo, P.a.lo, 4, dims, str, box, estr)) return false;
+        } else {
+            cuuint64_t rdims[4] = {(cuuint64_t)P.a_raw.c, (cuuint64_t)P.a_raw.w, (cuuint64_t)P.a_raw.h, (cuuint64_t)P.B};
+            cuuint64_t rstr[3] = {(cuuint64_t)P.a_raw.sW * 4, (cuuint64_t)P.a_raw.sH * 4, (cuuint64_t)P.a_raw.sN * 4};
+            if (!encode(plan.tmap_a_hi, P.a_raw.p, 4, rdims, rstr, box, estr, true)) return false;
         }
     }
     {
@@ -546,7 +539,8 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
 
 template <int BLOCK_N, int STAGES, int MODE, bool XF>
 static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
-    constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 16 + EP_WARPS * 32 * 32 * 4 + 1024;
+    constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 48 + EP_WARPS * 32 * 32 * 4 + 1024 +
+                         (XF ? 1024 + 2 * 128 * 64 * 4 : 0);
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr = false;
     if (!attr) {
@@ -569,9 +563,9 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
 template <int BLOCK_N, int STAGES>
 static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     if (P.in_scale) {  // transformed input: only the shapes the plan produces (1x1, plain or upsample epilogue)
-        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {
-            if (P.up2) launch_tm<BLOCK_N, STAGES, EPI_UP2, true>(P, plan, G, s);
-            else launch_tm<BLOCK_N, STAGES, EPI_PLAIN, true>(P, plan, G, s);
+        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {  // 2 operand stages: shared memory also holds the raw staging ring
+            if (P.up2) launch_tm<BLOCK_N, 2, EPI_UP2, true>(P, plan, G, s);
+            else launch_tm<BLOCK_N, 2, EPI_PLAIN, true>(P, plan, G, s);
             return;
         }
         throw Error(-1, "conv_tc: transformed input with unsupported tile shape");
