@@ -384,7 +384,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         make_float4(acc[c0 + 4 * g], acc[c0 + 4 * g + 1], acc[c0 + 4 * g + 2], acc[c0 + 4 * g + 3]);
                 __syncwarp();
                 const int ch = tn * BLOCK_N + cb + c0 + sub_g * 4;
-                constexpr int PB = MODE == EPI_UP2 ? 4 : 8;  // pixels-per-lane whose loads are in flight together
+                constexpr int PB = MODE == EPI_UP2 ? (XF ? 2 : 4) : 8;  // pixels-per-lane whose loads are in flight together
 #pragma unroll
                 for (int bt = 0; bt < 8 / PB; ++bt) {
                     int pv[PB], pn[PB], py[PB], px[PB];

@@ -735,11 +735,13 @@ k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
     if (nb > max_blobs) nb = max_blobs;
     HeapQ hp;
     hp.dist = dist;
-    // warp 0: large blobs, one after the other, with the large heap; warps 1..7: the small ones.
-    // Each heap region starts 2 slots in, so that slot index c = 4i-2 is 16-byte aligned.
-    const int pass = warp == 0 ? 0 : 1;
-    hp.s = (warp == 0 ? heaps : heaps + (big_cap + 4) + (size_t)(warp - 1) * (WT_SMALL_CAP + 4));
-    hp.cap = warp == 0 ? big_cap : WT_SMALL_CAP;
+    // warps 0,1: large blobs, one after the other, each with half of the large heap region;
+    // warps 2..7: the small ones.  (Slot index c = 4i-2 of every region is 16-byte aligned.)
+    const int pass = warp < 2 ? 0 : 1;
+    const int half_cap = ((big_cap + 4) / 2 - 4) & ~3;
+    hp.s = warp < 2 ? heaps + (size_t)warp * ((big_cap + 4) / 2)
+                    : heaps + (big_cap + 4) + (size_t)(warp - 1) * (WT_SMALL_CAP + 4);
+    hp.cap = warp < 2 ? half_cap : WT_SMALL_CAP;
     while (true) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&s_next[pass], 1);

@@ -1,0 +1,93 @@
+"""Row f1 (tile driver): patch geometry and stitching pinned against goldens produced by the
+reference's own `infer/tile.py` functions (oracle/gen_golden_tile.py); output-format checks."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from hover_net_b200.infer import tile
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "tile_*.npz"))))
+def test_patch_geometry_and_stitching_match_reference(path):
+    g = np.load(path)
+    win, msk, h, w = int(g["win"]), int(g["msk"]), int(g["h"]), int(g["w"])
+    img = np.random.default_rng(int(g["seed"])).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    padded, pinfo, corner = tile._prepare_patching(img, win, msk, True)
+    assert np.array_equal(pinfo, g["patch_info"]) and list(corner) == list(g["corner"])
+    assert np.array_equal(padded.shape, g["padded_shape"])
+    assert np.array_equal(padded.astype(np.int64).sum((1, 2)), g["padded_rowsum"])
+    data = []
+    for y, x, _, _ in pinfo:
+        yy, xx = np.mgrid[0:msk, 0:msk]
+        data.append(np.stack([yy + y, xx + x, (yy + y) * 1000 + (xx + x), np.full_like(yy, 7)], -1).astype(np.float32))
+    perm = np.random.default_rng(1).permutation(len(data))  # arrival order must not matter
+    m = tile._stitch([pinfo[i] for i in perm], [data[i] for i in perm], img.shape)
+    assert np.array_equal(m, g["stitched"])
+
+
+def test_json_writer_format(tmp_path):
+    from hover_net_b200.infer.base import InferManager
+    info = {3: {"bbox": np.array([[1, 2], [5, 9]]), "centroid": np.array([4.5, 2.25]),
+                "contour": np.array([[2, 1], [8, 1], [8, 4]], dtype=np.int32), "type_prob": 0.75, "type": 2},
+            7: {"bbox": np.array([[0, 0], [2, 2]]), "centroid": np.array([0.5, 0.5]),
+                "contour": np.array([[0, 0], [1, 0], [1, 1]], dtype=np.int32), "type_prob": None, "type": None}}
+    p = str(tmp_path / "a.json")
+    InferManager._save_json(None, p, info, None)
+    d = json.load(open(p))
+    assert d["mag"] is None and sorted(d["nuc"].keys()) == ["3", "7"]
+    assert d["nuc"]["3"] == {"bbox": [[1, 2], [5, 9]], "centroid": [4.5, 2.25], "contour": [[2, 1], [8, 1], [8, 4]],
+                             "type_prob": 0.75, "type": 2}
+    assert d["nuc"]["7"]["type"] is None
+
+
+@pytest.mark.gpu
+def test_process_file_list_end_to_end(tmp_path):
+    """Drive the whole tile pipeline on the device and cross-check it with the CPU oracle."""
+    import cv2
+    import scipy.io as sio
+    import torch
+    from hover_net_b200 import synth
+    from hover_net_b200.infer.tile import InferManager
+    from oracle import hovernet_torch as O
+    from oracle import postproc_oracle as P
+
+    mode, nt = "fast", 6
+    rng = np.random.default_rng(3)
+    big = np.concatenate([np.concatenate(list(synth.make_patches(2, 256, seed=40 + r)), 1) for r in range(2)], 0)
+    img = big[:300, :420].copy()  # 300x420 RGB -> 2x3 patches
+    os.makedirs(tmp_path / "in")
+    cv2.imwrite(str(tmp_path / "in" / "tileA.png"), cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+    sd = synth.make_state_dict(mode, nt, seed=0)
+    mgr = InferManager(method={"model_args": {"nr_types": nt, "mode": mode}, "model_path": sd}, type_info_path=None)
+    mgr.process_file_list({"batch_size": 4, "nr_inference_workers": 0, "nr_post_proc_workers": 0,
+                           "patch_input_shape": 256, "patch_output_shape": 164, "input_dir": str(tmp_path / "in"),
+                           "output_dir": str(tmp_path / "out"), "mem_usage": 0.1, "draw_dot": True,
+                           "save_qupath": True, "save_raw_map": True})
+    mat = sio.loadmat(str(tmp_path / "out" / "mat" / "tileA.mat"))
+    js = json.load(open(str(tmp_path / "out" / "json" / "tileA.json")))
+    assert os.path.exists(str(tmp_path / "out" / "overlay" / "tileA.png"))
+    assert open(str(tmp_path / "out" / "qupath" / "tileA.tsv")).readline() == "x\ty\tclass\tname\tcolor\n"
+    raw, inst = mat["raw_map"], mat["inst_map"]
+    assert raw.shape == (300, 420, 4) and inst.shape == (300, 420) and inst.dtype == np.int32
+    # (1) stitched float map vs the CPU oracle run over the same patch grid
+    padded, pinfo, _ = tile._prepare_patching(img, 256, 164, True)
+    tsd = O.to_torch_state_dict(sd)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    outs = O.infer_step(np.stack([padded[y:y + 256, x:x + 256] for y, x, _, _ in pinfo]), tsd, mode, nt)
+    ref_map = tile._stitch(list(pinfo), list(outs), img.shape)
+    assert np.abs(raw[..., 1:] - ref_map[..., 1:]).max() <= 1e-4
+    # (2) instances: oracle post-processing of the device-produced map must agree bit for bit
+    oi, oinfo = P.process(raw, nr_types=nt, return_centroids=True)
+    assert np.array_equal(inst, oi)
+    assert sorted(int(k) for k in js["nuc"]) == sorted(oinfo.keys())
+    for k, v in oinfo.items():
+        j = js["nuc"][str(k)]
+        assert j["bbox"] == v["bbox"].tolist() and j["centroid"] == v["centroid"].tolist()
+        assert j["contour"] == v["contour"].tolist() and j["type"] == v["type"] and j["type_prob"] == v["type_prob"]
+    assert np.array_equal(mat["inst_uid"].ravel(), np.array(sorted(oinfo.keys())))
+    mgr.net.ctx.close()
