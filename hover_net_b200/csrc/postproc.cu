@@ -780,8 +780,11 @@ k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
         }
         if (lane == 0) {
             unsigned int age = 1;
+            const long long t0 = clock64();
+            int npop = 0;
             while (hp.n > 0) {
                 const u64 e = hp.pop();
+                ++npop;
                 const int idx = (int)((unsigned int)e & 0xffffu);
                 const int y = (int)__umulhi((unsigned int)idx, wmagic), x = idx - y * W;
                 const short lab = state[idx];
@@ -800,6 +803,157 @@ k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
                         hp.push(((u64)kq[j] << 32) | (u64)((age << 16) | (unsigned int)q[j]));
                     }
             }
+            atomicAdd(&st[m].pad[0], npop);                                  // diagnostics: pops / flood cycles per map
+            atomicMax(&st[m].pad[1], (int)((clock64() - t0) >> 10));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < N; p += blockDim.x) { short v = state[p]; inst[p] = v > 0 ? (int)v : 0; }
+}
+
+// Calendar-queue variant of the per-map flood (used when the fp32 priority table fits in shared memory).
+// The heap is replaced by NB buckets over the map's priority range (bucket index monotone in the
+// priority), each an exactly-ordered singly linked list threaded through next[px], plus a two-level
+// bitmap of non-empty buckets: pop = two find-first-set + unlink the head, push = walk the (short)
+// bucket list to the insertion point.  Ordering inside a bucket uses the same exact comparison as the
+// heap (fp32 key, then fp64 priority); an entry is placed after all entries with an equal priority,
+// i.e. in push (= age) order.  The pop sequence is therefore again the (value, age) order.
+constexpr int WC_NB_BIG = 2048, WC_NB_SMALL = 256;
+constexpr unsigned short WC_NIL = 0xffffu;
+
+__global__ void __launch_bounds__(WT_WARPS * 32)
+k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigned char *__restrict__ fg_all,
+                const int *__restrict__ L1_all, const int *__restrict__ size1_all, const int *__restrict__ blob_root_all,
+                const int4 *__restrict__ bbox_all, const int2 *__restrict__ range_all, int max_blobs,
+                int *__restrict__ inst_all, PPStats *st) {
+    extern __shared__ __align__(16) unsigned char wc_smem[];
+    __shared__ int s_next[2];
+    __shared__ unsigned int s_kmin, s_kmax;
+    const unsigned int wmagic = (unsigned int)((0x100000000ull + (unsigned)W - 1) / (unsigned)W);
+    const int m = blockIdx.x, N = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n2 = ((size_t)N * 2 + 15) & ~(size_t)15, n4 = ((size_t)N * 4 + 15) & ~(size_t)15;
+    float *kk = reinterpret_cast<float *>(wc_smem);
+    short *state = reinterpret_cast<short *>(wc_smem + n4);
+    unsigned short *nxt = reinterpret_cast<unsigned short *>(wc_smem + n4 + n2);
+    unsigned char *qbase = wc_smem + n4 + 2 * n2;
+    // per-warp queue storage: heads u16[NB] | bitmap u32[NB/32]
+    const int NB = warp < 2 ? WC_NB_BIG : WC_NB_SMALL;
+    const size_t big_bytes = WC_NB_BIG * 2 + WC_NB_BIG / 8, small_bytes = WC_NB_SMALL * 2 + WC_NB_SMALL / 8;
+    unsigned char *mine = qbase + (warp < 2 ? warp * big_bytes : 2 * big_bytes + (warp - 2) * small_bytes);
+    unsigned short *head = reinterpret_cast<unsigned short *>(mine);
+    unsigned int *bitmap = reinterpret_cast<unsigned int *>(mine + NB * 2);
+    const double *dist = dist_all + (size_t)m * N;
+    const unsigned char *fg = fg_all + (size_t)m * N;
+    const int *L1 = L1_all + (size_t)m * N;
+    int *inst = inst_all + (size_t)m * N;
+    if (threadIdx.x == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_next[0] = s_next[1] = 0; }
+    __syncthreads();
+    unsigned int lmin = 0xffffffffu, lmax = 0u;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const bool f = fg[p] != 0;
+        state[p] = f ? (short)inst[p] : (short)-1;
+        const float kv = (float)dist[p] + 0.0f;  // +0.0f: -0.0 and +0.0 are equal priorities, give them one key
+        kk[p] = kv;
+        if (f) { const unsigned int ky = fkey(kv); lmin = min(lmin, ky); lmax = max(lmax, ky); }
+    }
+    for (int o = 16; o; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if (lane == 0) { atomicMin(&s_kmin, lmin); atomicMax(&s_kmax, lmax); }
+    for (int i = lane; i < NB; i += 32) head[i] = WC_NIL;
+    for (int i = lane; i < NB / 32; i += 32) bitmap[i] = 0u;
+    __syncthreads();
+    const float kmin = fkey_inv(s_kmin), kmax = fkey_inv(s_kmax);
+    const float scale = kmax > kmin ? (float)NB / (kmax - kmin) : 0.f;
+    int nb = st[m].nblobs;
+    if (nb > max_blobs) nb = max_blobs;
+    const int pass = warp < 2 ? 0 : 1;
+    u64 summary = 0ull;  // bit j <=> bitmap[j] != 0   (NB/32 <= 64 words)
+
+    auto bucket_of = [&](float k) {
+        int b = (int)((k - kmin) * scale);
+        return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+    };
+    auto precedes = [&](int a, int b) {  // strict exact order of pixel a before pixel b (equal => false)
+        const float ka = kk[a], kb = kk[b];
+        if (ka != kb) return ka < kb;
+        return dist[a] < dist[b];
+    };
+    auto q_push = [&](int q) {
+        const int b = bucket_of(kk[q]);
+        unsigned short cur = head[b];
+        if (cur == WC_NIL) {
+            head[b] = (unsigned short)q; nxt[q] = WC_NIL;
+            bitmap[b >> 5] |= 1u << (b & 31);
+            summary |= 1ull << (b >> 5);
+            return;
+        }
+        if (precedes(q, cur)) { nxt[q] = cur; head[b] = (unsigned short)q; return; }
+        unsigned short prev = cur;
+        cur = nxt[cur];
+        while (cur != WC_NIL && !precedes(q, cur)) { prev = cur; cur = nxt[cur]; }
+        nxt[q] = cur; nxt[prev] = (unsigned short)q;
+    };
+    auto q_pop = [&]() {
+        const int j = __ffsll((long long)summary) - 1;
+        const unsigned int w = bitmap[j];
+        const int bit = __ffs((int)w) - 1, b = j * 32 + bit;
+        const unsigned short p = head[b], nx = nxt[p];
+        head[b] = nx;
+        if (nx == WC_NIL) {
+            const unsigned int w2 = w & ~(1u << bit);
+            bitmap[j] = w2;
+            if (!w2) summary &= ~(1ull << j);
+        }
+        return (int)p;
+    };
+
+    while (true) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&s_next[pass], 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= nb) break;
+        const int root = blob_root_all[(size_t)m * max_blobs + k];
+        const int bsize = size1_all[(size_t)m * N + root];
+        if ((bsize >= WT_BIG) != (pass == 0)) continue;
+        { const int2 rg = range_all[(size_t)m * max_blobs + k]; if (rg.y == 0 || rg.x == rg.y) continue; }
+        const int4 bb = bbox_all[(size_t)m * max_blobs + k];
+        const int bw = bb.w - bb.y + 1, bh = bb.z - bb.x + 1, area = bw * bh;
+        for (int base = 0; base < area; base += 32) {  // marker pixels in raster order
+            int i = base + lane;
+            bool is = false;
+            int p = 0;
+            if (i < area) {
+                int yy = bb.x + i / bw, xx = bb.y + i % bw;
+                p = yy * W + xx;
+                is = state[p] > 0 && L1[p] == root;
+            }
+            unsigned int msk = __ballot_sync(0xffffffffu, is);
+            while (msk) {
+                int src = __ffs(msk) - 1;
+                msk &= msk - 1;
+                int pp = __shfl_sync(0xffffffffu, p, src);
+                if (lane == 0) q_push(pp);
+            }
+        }
+        if (lane == 0) {
+            const long long t0 = clock64();
+            int npop = 0;
+            while (summary) {
+                const int idx = q_pop();
+                ++npop;
+                const int y = (int)__umulhi((unsigned int)idx, wmagic), x = idx - y * W;
+                const short lab = state[idx];
+                const int q[4] = {y > 0 ? idx - W : -1, x > 0 ? idx - 1 : -1, x < W - 1 ? idx + 1 : -1, y < H - 1 ? idx + W : -1};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)  // up, left, right, down; label at push time
+                    if (q[j] >= 0 && state[q[j]] == 0) { state[q[j]] = lab; q_push(q[j]); }
+            }
+            atomicAdd(&st[m].pad[0], npop);
+            atomicMax(&st[m].pad[1], (int)((clock64() - t0) >> 10));
         }
         __syncwarp();
     }
@@ -891,6 +1045,9 @@ __global__ void k_table_rows(const InstAcc *__restrict__ acc_all, const int *__r
 }
 
 // ------------------------------------------------------------------------------------------------
+static int g_flood_impl = 0;  // 0 auto (calendar queue > shared-memory heap > global heap), 1 no calendar queue, 2 global only
+void postproc_set_flood_impl(int v) { g_flood_impl = v; }
+
 template <typename A>
 static void pp_layout(A &ar, PostprocBuffers &b, int n, int H, int W, int nr_types) {
     size_t N = (size_t)H * W, T = (size_t)n * N;
@@ -999,18 +1156,24 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
         // patch-sized maps: per-map CTA with the flood state in shared memory; otherwise the generic kernel
         const size_t budget = 225 * 1024;
         const size_t state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15), kk_bytes = (((size_t)N * 4 + 15) & ~(size_t)15);
+        const size_t cal_bytes = kk_bytes + 2 * state_bytes + 2 * (WC_NB_BIG * 2 + WC_NB_BIG / 8) +
+                                 (WT_WARPS - 2) * (WC_NB_SMALL * 2 + WC_NB_SMALL / 8);
         const size_t small_bytes = (size_t)(WT_WARPS - 1) * (WT_SMALL_CAP + 4) * 8;
         const bool use_kk = state_bytes + kk_bytes + small_bytes + (2048 + 4) * 8 <= budget;
         const size_t fixed = state_bytes + (use_kk ? kk_bytes : 0) + small_bytes;
         long long cap = fixed + 64 < budget ? (long long)((budget - fixed) / 8) - 4 : 0;
         cap = std::min<long long>(cap & ~3ll, 16384);
-        if (cap >= 1024 && N < 65536 && b.max_ids < 32000) {
-            static bool attr = false;
-            if (!attr) {
-                HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
-                HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
-                attr = true;
-            }
+        static bool attr = false;
+        if (!attr) {
+            HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
+            HVN_CUDA(cudaFuncSetAttribute(k_watershed_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
+            HVN_CUDA(cudaFuncSetAttribute(k_watershed_cal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget + 64));
+            attr = true;
+        }
+        if (cal_bytes <= budget && N < 65535 && b.max_ids < 32000 && g_flood_impl == 0) {
+            L(k_watershed_cal<<<n, WT_WARPS * 32, cal_bytes, stream>>>(H, W, b.dist, b.fg, b.L1, b.size1, b.blob_root, (int4 *)b.bbox,
+                                                                        (const int2 *)b.lab_range, b.max_blobs, inst, st));
+        } else if (cap >= 1024 && N < 65536 && b.max_ids < 32000 && g_flood_impl <= 1) {
             size_t smem = fixed + (size_t)(cap + 4) * 8;
             if (use_kk)
                 L(k_watershed_tile<true><<<n, WT_WARPS * 32, smem, stream>>>(H, W, (int)cap, b.dist, b.fg, b.L1, b.size1, b.blob_root,
@@ -1042,6 +1205,14 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
             *prof += line;
         }
         for (auto &e : evs) cudaEventDestroy(e.second);
+        std::vector<PPStats> hs(n);
+        HVN_CUDA(cudaMemcpy(hs.data(), st, sizeof(PPStats) * n, cudaMemcpyDeviceToHost));
+        long long pops = 0; int pmax = 0, cmax = 0, bl = 0, bmax = 0;
+        for (auto &h : hs) { pops += h.pad[0]; pmax = std::max(pmax, h.pad[0]); cmax = std::max(cmax, h.pad[1]); bl += h.nblobs; bmax = std::max(bmax, h.nblobs); }
+        char line[256];
+        snprintf(line, sizeof(line), "pp stats: maps %d  flood pops total %lld  max/map %d  longest single flood %d kcycles  blobs total %d max/map %d\n",
+                 n, pops, pmax, cmax, bl, bmax);
+        *prof += line;
     }
     return launches;
 }

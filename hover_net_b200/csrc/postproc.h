@@ -18,6 +18,7 @@ struct PostprocBuffers {
     int *tcnt = nullptr;
 };
 
+void postproc_set_flood_impl(int v);  // test hook: 0 auto, 1 shared-memory heap, 2 global-memory heap
 size_t postproc_workspace_bytes(int n, int H, int W, int nr_types);
 
 // pred [n,H,W,C] f32 (device) -> inst [n,H,W] i32, table [n,max_rows,10] i64, n_rows [n] i32 (device).

@@ -86,3 +86,21 @@ def test_idempotent_and_batch_invariant(ctx):
     one = ctx.postproc(maps[3], 6)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     assert np.array_equal(a[0][3], one[0][0]) and int(a[2][3]) == int(one[2][0])
+
+
+def test_three_flood_implementations_agree(ctx, oracle_pp):
+    """calendar queue (default) == shared-memory heap == global-memory heap == oracle."""
+    import cv2
+    rng = np.random.default_rng(9)
+    maps = [synth.synth_pred_map(164, 164, None, s, density=1.0 / 350.0) for s in range(3)]  # crowded: touching nuclei
+    for _ in range(3):
+        m = np.stack([cv2.GaussianBlur(rng.standard_normal((164, 164)), (0, 0), s) for s in (5, 3, 3)], -1)
+        m = m / np.abs(m).max((0, 1))
+        m[..., 0] = 0.55 + 0.5 * m[..., 0]
+        maps.append(m.astype(np.float32))
+    try:
+        for impl in (0, 1, 2):
+            ctx.set_option("flood_impl", impl)
+            _check(ctx, oracle_pp, maps, None)
+    finally:
+        ctx.set_option("flood_impl", 0)

@@ -147,9 +147,10 @@ def ppprof(B=64):
     for name, maps in (("cnn-output", pred), ("synthetic nuclei", np.stack([synth.synth_pred_map(164, 164, 6, s) for s in range(B)]))):
         net.ctx.postproc(maps, 6); net.ctx.postproc(maps, 6)
         print("== %s: total %.3f ms for %d maps" % (name, net.ctx.stage_ms("postproc"), B))
-        rows = [l for l in net.ctx.debug_log().split("\n") if l.startswith("pp ")]
+        rows = [l for l in net.ctx.debug_log().split("\n") if l.startswith("pp ") and "stats" not in l]
         rows.sort(key=lambda l: -float(l.split()[-2]))
         print("\n".join(rows[:8]))
+        print("\n".join(l for l in net.ctx.debug_log().split("\n") if "pp stats" in l))
     net.ctx.close()
 
 
