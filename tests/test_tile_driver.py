@@ -91,3 +91,43 @@ def test_process_file_list_end_to_end(tmp_path):
         assert j["contour"] == v["contour"].tolist() and j["type"] == v["type"] and j["type_prob"] == v["type_prob"]
     assert np.array_equal(mat["inst_uid"].ravel(), np.array(sorted(oinfo.keys())))
     mgr.net.ctx.close()
+
+
+@pytest.mark.gpu
+def test_config0_single_270_tile_original_seg_only():
+    """BASELINE configs[0]: one 270x270x3 tile, seg-only, `original` mode: U1 (one network patch) and
+    U2 (tile-driver semantics: 4x4 patches of 270 stitched to 320^2, cropped to 270^2) vs the CPU oracle."""
+    import torch
+    from hover_net_b200 import synth
+    from hover_net_b200.infer.tile import InferManager
+    from oracle import hovernet_torch as O
+    from oracle import postproc_oracle as P
+
+    mode, nt = "original", None
+    sd = synth.make_state_dict(mode, nt, seed=0)
+    img = synth.make_patches(1, 270, seed=77)[0]
+    mgr = InferManager(method={"model_args": {"nr_types": nt, "mode": mode}, "model_path": sd}, type_info_path=None)
+    mgr.patch_input_shape, mgr.patch_output_shape, mgr.batch_size = 270, 80, 16
+    tsd = O.to_torch_state_dict(sd)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    # U1: the tile itself is exactly one network patch
+    out = mgr.run_step(img[None])
+    ref = O.infer_step(img[None], tsd, mode, nt)
+    assert out.shape == (1, 80, 80, 3) and np.abs(out - ref).max() <= 1e-4
+    oi, _ = P.process(out[0], nr_types=None, return_centroids=True)
+    gi, _ = mgr.post_proc_func(out[0], nr_types=None, return_centroids=True)
+    assert np.array_equal(gi, oi)
+    # U2: tile-driver semantics
+    pred_map, pred_inst, info = mgr.infer_image(img)
+    assert pred_map.shape == (270, 270, 3) and pred_inst.shape == (270, 270)
+    padded, pinfo, _ = tile._prepare_patching(img, 270, 80, True)
+    assert len(pinfo) == 16
+    outs = O.infer_step(np.stack([padded[y:y + 270, x:x + 270] for y, x, _, _ in pinfo]), tsd, mode, nt)
+    ref_map = tile._stitch(list(pinfo), list(outs), img.shape)
+    assert np.abs(pred_map - ref_map).max() <= 1e-4
+    oi, oinfo = P.process(pred_map, nr_types=None, return_centroids=True)
+    assert np.array_equal(pred_inst, oi) and sorted(info.keys()) == sorted(oinfo.keys())
+    for k in info:
+        assert np.array_equal(info[k]["bbox"], oinfo[k]["bbox"]) and np.array_equal(info[k]["centroid"], oinfo[k]["centroid"])
+        assert np.array_equal(info[k]["contour"], oinfo[k]["contour"]) and info[k]["type"] is None
+    mgr.net.ctx.close()
