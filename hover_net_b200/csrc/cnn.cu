@@ -163,6 +163,31 @@ void Model::make_conv(const std::string &name, int groups) {
     conv_[name] = cw;
 }
 
+// two 1x1 convolutions with the same cout, concatenated along K: [cout][cin1 + cin2]
+void Model::make_conv_concat(const std::string &key, const std::string &name1, const std::string &name2) {
+    const ParamSpec &s1 = spec[index.at(name1)], &s2 = spec[index.at(name2)];
+    const std::vector<float> &w1 = hostp(name1), &w2 = hostp(name2);
+    const int O = (int)s1.shape[0], I1 = (int)s1.shape[1], I2 = (int)s2.shape[1];
+    HVN_CHECK(s2.shape[0] == O && s1.shape[2] == 1 && s2.shape[2] == 1 && I1 % 64 == 0 && I2 % 64 == 0, -1,
+              "internal: cannot concatenate " + name1 + " and " + name2);
+    ConvWeights cw;
+    cw.taps = 1; cw.kh = cw.kw = 1; cw.cout = O; cw.cin = I1 + I2; cw.cin_pad = I1 + I2;
+    size_t n = (size_t)O * cw.cin_pad;
+    std::vector<__half> hi(n), lo(n);
+    for (int o = 0; o < O; ++o)
+        for (int i = 0; i < I1 + I2; ++i) {
+            float v = i < I1 ? w1[(size_t)o * I1 + i] : w2[(size_t)o * I2 + (i - I1)];
+            __half h = __float2half_rn(v);
+            hi[(size_t)o * cw.cin_pad + i] = h;
+            lo[(size_t)o * cw.cin_pad + i] = __float2half_rn(v - __half2float(h));
+        }
+    cw.hi = dalloc<__half>(n, wallocs_, false);
+    cw.lo = dalloc<__half>(n, wallocs_, false);
+    HVN_CUDA(cudaMemcpy(cw.hi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    HVN_CUDA(cudaMemcpy(cw.lo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    conv_[key] = cw;
+}
+
 // eval-mode BatchNorm2d(eps=1e-5) as y = x*scale + shift
 void Model::make_bn(const std::string &p) {
     const auto &g = hostp(p + ".weight"), &b = hostp(p + ".bias"), &m = hostp(p + ".running_mean"),
@@ -221,6 +246,10 @@ void Model::finalize() {
         } else if (n.size() > 13 && n.compare(n.size() - 13, 13, ".running_mean") == 0) {
             make_bn(n.substr(0, n.size() - 13));
         }
+    }
+    for (auto &g : kGroups) {
+        const std::string gn = g.name;
+        make_conv_concat(gn + ".fused3", gn + ".units.0.conv3.weight", gn + ".shortcut.weight");
     }
     finalized = true;
 }
@@ -348,7 +377,7 @@ Plan &Model::plan(int B, int H, int W) {
     HVN_CHECK(finalized, -5, "weights not finalised (call hvn_finalize_weights)");
     HVN_CHECK(H == W, -1, "only square patches are supported (reference patch geometry is square)");
     std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "p" + std::to_string(conv_path) +
-                      "b" + std::to_string(branch_streams) + "x" + std::to_string(xform);
+                      "b" + std::to_string(branch_streams) + "x" + std::to_string(xform) + "f" + std::to_string(fuse_shortcut);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     std::unique_ptr<Plan> pl(new Plan());
@@ -426,7 +455,8 @@ Plan &Model::plan(int B, int H, int W) {
         int so = (si + g.stride - 1) / g.stride;
         RawRef S = new_raw(so, so, g.c3);
         SplitRef A1 = new_split(si, si, g.c1), A2 = new_split(so, so, g.c1), Pp = new_split(so, so, g.c3);
-        { Op &op = add_conv(gn + ".shortcut.weight", x, g.stride, 0, so, so); op.cp.out_raw = S; }
+        const bool fuse = fuse_shortcut != 0;
+        if (!fuse) { Op &op = add_conv(gn + ".shortcut.weight", x, g.stride, 0, so, so); op.cp.out_raw = S; }
         for (int u = 0; u < g.units; ++u) {
             std::string p = gn + ".units." + std::to_string(u) + ".";
             const SplitRef &in = u == 0 ? x : Pp;
@@ -446,7 +476,12 @@ Plan &Model::plan(int B, int H, int W) {
             { Op &op = add_conv(p + "conv2.weight", a1, st, lo, so, so); set_bn(op, p + "conv2/bn", A2); }
             {
                 Op &op = add_conv(p + "conv3.weight", A2, 1, 0, so, so);
-                op.cp.res = S;
+                if (u == 0 && fuse) {  // conv3(a2) + shortcut(x) as one GEMM over K = [c1 | cin]
+                    op.cp.w = conv_.at(gn + ".fused3");
+                    op.cp.a2 = x; op.cp.a2_stride = g.stride; op.cp.cin1 = g.c1;
+                    op.flops += 2.0 * B * so * so * (double)g.cin * g.c3;
+                    op.name = gn + ".units.0.conv3+shortcut";
+                } else op.cp.res = S;
                 if (u + 1 < g.units) {
                     op.cp.out_raw = S;
                     if (!use_xf) set_bn(op, gn + ".units." + std::to_string(u + 1) + ".preact/bn", Pp);

@@ -61,6 +61,7 @@ class Model {
     std::map<std::string, int> index;
     std::map<std::string, std::vector<float>> host;
     bool finalized = false;
+    int fuse_shortcut = 1;   // fold each residual group's 1x1 shortcut into unit 0's conv3 (one GEMM over [a2 | x])
     int xform = 1;           // fuse pre-activation BN+ReLU into the consuming 1x1 conv's A-operand load
     int branch_streams = 1;  // run the decoder branches on separate streams
     int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only, 2 auto + per-layer self test
@@ -96,6 +97,7 @@ class Model {
     void add_bn(const std::string &prefix, int c);
     const std::vector<float> &hostp(const std::string &name) const;
     void make_conv(const std::string &name, int groups);
+    void make_conv_concat(const std::string &key, const std::string &name1, const std::string &name2);
     void make_bn(const std::string &prefix);
     template <typename T> T *dalloc(size_t n, std::vector<void *> &owner, bool zero);
 };

@@ -32,6 +32,7 @@ void launch_head(const HeadParams &P, cudaStream_t s);
 struct TcPlan {
     bool ok = false;
     unsigned char tmap_a_hi[128], tmap_a_lo[128], tmap_w_hi[128], tmap_w_lo[128];
+    unsigned char tmap_a2_hi[128], tmap_a2_lo[128];  // second GEMM source (fused shortcut), if any
     int bw = 0, bh = 0;          // M-tile = bw x bh output pixels of one image
     int tiles_x = 0, tiles_y = 0;
     int block_n = 0;

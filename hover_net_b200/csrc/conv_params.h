@@ -33,6 +33,11 @@ struct ConvParams {
     // from a pre-transformed split tensor.  `a` must then describe the same view (used by the referee).
     RawRef a_raw;
     const float *in_scale = nullptr, *in_shift = nullptr;
+    // Optional second GEMM source accumulated into the same output tile (a residual group's 1x1 shortcut
+    // convolution fused into unit 0's conv3): D += A2[pixel * a2_stride] . W[:, cin1 : cin1 + a2.c].
+    // `w` then holds both weight matrices concatenated along K (cin = cin1 + a2.c, 1 tap, no padding).
+    SplitRef a2;
+    int a2_stride = 1, cin1 = 0;
     ConvWeights w;
     int stride = 1, pad_t = 0, pad_l = 0;
     int B = 0, ho = 0, wo = 0;

@@ -47,11 +47,51 @@ __global__ void __launch_bounds__(256) k_conv_ref(const ConvParams P) {
         bool inb = pvalid && iy >= 0 && iy < P.a.h && ix >= 0 && ix < P.a.w;
         long long aoff = ln * P.a.sN + (long long)iy * P.a.sH + (long long)ix * P.a.sW;
         long long woff = ((long long)tap * P.w.cout + (n0 + lp)) * P.w.cin_pad;
-        for (int c0 = 0; c0 < P.w.cin; c0 += RF_BK) {
+        const int cend = P.a2.hi ? P.cin1 : P.w.cin;
+        for (int c0 = 0; c0 < cend; c0 += RF_BK) {
             float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
             if (inb) {
                 uint2 h = *reinterpret_cast<const uint2 *>(P.a.hi + aoff + c0 + kq);
                 uint2 l = *reinterpret_cast<const uint2 *>(P.a.lo + aoff + c0 + kq);
+                const __half *hh = reinterpret_cast<const __half *>(&h);
+                const __half *ll = reinterpret_cast<const __half *>(&l);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a4[i] = join_f16(hh[i], ll[i]);
+            }
+            if (nvalid) {
+                uint2 h = *reinterpret_cast<const uint2 *>(P.w.hi + woff + c0 + kq);
+                uint2 l = *reinterpret_cast<const uint2 *>(P.w.lo + woff + c0 + kq);
+                const __half *hh = reinterpret_cast<const __half *>(&h);
+                const __half *ll = reinterpret_cast<const __half *>(&l);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b4[i] = join_f16(hh[i], ll[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { As[kq + i][lp] = a4[i]; Bs[kq + i][lp] = b4[i]; }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RF_BK; ++k) {
+                float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+                float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+                float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    if (P.a2.hi) {  // second source (fused 1x1 shortcut): pixel (oy*s2, ox*s2), weights at K offset cin1
+        const int iy = loy * P.a2_stride, ix = lox * P.a2_stride;
+        const bool inb = pvalid && iy < P.a2.h && ix < P.a2.w;
+        const long long aoff = ln * P.a2.sN + (long long)iy * P.a2.sH + (long long)ix * P.a2.sW;
+        const long long woff = (long long)(n0 + lp) * P.w.cin_pad + P.cin1;
+        for (int c0 = 0; c0 < P.a2.c; c0 += RF_BK) {
+            float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (inb) {
+                uint2 h = *reinterpret_cast<const uint2 *>(P.a2.hi + aoff + c0 + kq);
+                uint2 l = *reinterpret_cast<const uint2 *>(P.a2.lo + aoff + c0 + kq);
                 const __half *hh = reinterpret_cast<const __half *>(&h);
                 const __half *ll = reinterpret_cast<const __half *>(&l);
 #pragma unroll

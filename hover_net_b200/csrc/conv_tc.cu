@@ -108,6 +108,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 struct TcGeom {
     int flat, bw, bh, tiles_x, tiles_y, tiles_m, tiles_n, kchunks, seg;
+    int k1;  // > 0: K-slices [0,k1) come from the first source, [k1,kchunks) from the second (fused shortcut)
     long long m_total;
 };
 
@@ -122,6 +123,7 @@ template <int BLOCK_N, int STAGES, int MODE, bool XF>
 __global__ void __launch_bounds__(TC_THREADS + (XF ? XF_WARPS * 32 : 0), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+          const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
           const ConvParams P, const TcGeom G) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int STAGE_BYTES = tc_stage_bytes<BLOCK_N>();
@@ -199,6 +201,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     const int tap = it / G.kchunks, kc = it - tap * G.kchunks;
                     if constexpr (XF) {
                         // A tiles are written by the transform warps
+                    } else if (G.k1 > 0 && kc >= G.k1) {  // second source: fused 1x1 shortcut on the block input
+                        const int c2 = (kc - G.k1) * 64;
+                        if (G.flat) {
+                            tma_2d(a_hi, &tm_a2_hi, full_bar(s), c2, (int)m0);
+                            tma_2d(a_lo, &tm_a2_lo, full_bar(s), c2, (int)m0);
+                        } else {
+                            tma_4d(a_hi, &tm_a2_hi, full_bar(s), c2, x0 * P.a2_stride, y0 * P.a2_stride, n_img);
+                            tma_4d(a_lo, &tm_a2_lo, full_bar(s), c2, x0 * P.a2_stride, y0 * P.a2_stride, n_img);
+                        }
                     } else if (G.flat) {
                         tma_2d(a_hi, &tm_a_hi, full_bar(s), kc * 64, (int)m0);
                         tma_2d(a_lo, &tm_a_lo, full_bar(s), kc * 64, (int)m0);
@@ -466,6 +477,12 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     if (w.cin_pad % 64 != 0 || w.cout % 32 != 0) return false;
     if (P.stride != 1 && P.stride != 2) return false;
     if (P.pad_t != P.pad_l) return false;
+    const bool two = P.a2.hi != nullptr;
+    if (two) {
+        if (w.taps != 1 || P.stride != 1 || P.pad_t != 0 || P.in_scale || (P.cin1 % 64) || (P.a2.c % 64)) return false;
+        if ((reinterpret_cast<uintptr_t>(P.a2.hi) & 15) || (reinterpret_cast<uintptr_t>(P.a2.lo) & 15)) return false;
+        if ((P.a2.sW % 8) || (P.a2.sH % 8) || (P.a2.sN % 8)) return false;
+    }
     const bool xf = P.in_scale != nullptr;
     if (xf) {
         if (w.taps != 1 || P.stride != 1 || P.pad_t != 0 || P.res.p) return false;
@@ -483,6 +500,10 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
                                : ((long long)P.a.sW * P.a.w == P.a.sH && (long long)P.a.sH * P.a.h == P.a.sN);
     const int ah = xf ? P.a_raw.h : P.a.h, aw = xf ? P.a_raw.w : P.a.w;
     plan.flat = (w.taps == 1 && P.stride == 1 && P.pad_t == 0 && dense_rows && P.ho == ah && P.wo == aw) ? 1 : 0;
+    if (two) {  // both sources must share the tile -> pixel mapping
+        const bool dense2 = (long long)P.a2.sW * P.a2.w == P.a2.sH && (long long)P.a2.sH * P.a2.h == P.a2.sN;
+        if (!(P.a2_stride == 1 && dense2 && P.a2.h == P.ho && P.a2.w == P.wo)) plan.flat = 0;
+    }
     if (xf && bn != 128 && bn != 64) return false;
     cuuint32_t ones[4] = {1, 1, 1, 1};
     if (plan.flat) {
@@ -498,6 +519,12 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
             if (!encode(plan.tmap_a_hi, P.a_raw.p, 2, rdims, rstr, box, ones, true)) return false;
         }
         plan.bw = 128; plan.bh = 1; plan.tiles_x = plan.tiles_y = 0;
+        if (two) {
+            cuuint64_t d2[2] = {(cuuint64_t)P.a2.c, (cuuint64_t)((long long)P.B * P.a2.h * P.a2.w)};
+            cuuint64_t s2[1] = {(cuuint64_t)P.a2.sW * 2};
+            if (!encode(plan.tmap_a2_hi, P.a2.hi, 2, d2, s2, box, ones)) return false;
+            if (!encode(plan.tmap_a2_lo, P.a2.lo, 2, d2, s2, box, ones)) return false;
+        }
     } else {
         // choose the (bw x bh <= 128) pixel rectangle that wastes the fewest accumulator rows
         int best_bw = 0, best_bh = 0;
@@ -524,6 +551,16 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
             cuuint64_t rdims[4] = {(cuuint64_t)P.a_raw.c, (cuuint64_t)P.a_raw.w, (cuuint64_t)P.a_raw.h, (cuuint64_t)P.B};
             cuuint64_t rstr[3] = {(cuuint64_t)P.a_raw.sW * 4, (cuuint64_t)P.a_raw.sH * 4, (cuuint64_t)P.a_raw.sN * 4};
             if (!encode(plan.tmap_a_hi, P.a_raw.p, 4, rdims, rstr, box, estr, true)) return false;
+        }
+        if (two) {
+            const int s2 = P.a2_stride;
+            if (plan.bw * s2 > 256 || plan.bh * s2 > 256) return false;
+            cuuint64_t d2[4] = {(cuuint64_t)P.a2.c, (cuuint64_t)P.a2.w, (cuuint64_t)P.a2.h, (cuuint64_t)P.B};
+            cuuint64_t st2[3] = {(cuuint64_t)P.a2.sW * 2, (cuuint64_t)P.a2.sH * 2, (cuuint64_t)P.a2.sN * 2};
+            cuuint32_t box2[4] = {64, (cuuint32_t)(plan.bw * s2), (cuuint32_t)(plan.bh * s2), 1};
+            cuuint32_t es2[4] = {1, (cuuint32_t)s2, (cuuint32_t)s2, 1};
+            if (!encode(plan.tmap_a2_hi, P.a2.hi, 4, d2, st2, box2, es2)) return false;
+            if (!encode(plan.tmap_a2_lo, P.a2.lo, 4, d2, st2, box2, es2)) return false;
         }
     }
     {
@@ -554,10 +591,11 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     int grid = std::min(G.tiles_m * G.tiles_n, sms);
-    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    CUtensorMap a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo;
     memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
     memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
-    k_conv_tc<BLOCK_N, STAGES, MODE, XF><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
+    memcpy(&a2_hi, plan.tmap_a2_hi, 128); memcpy(&a2_lo, plan.tmap_a2_lo, 128);
+    k_conv_tc<BLOCK_N, STAGES, MODE, XF><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
 }
 
 template <int BLOCK_N, int STAGES>
@@ -580,6 +618,7 @@ void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     G.flat = plan.flat; G.bw = plan.bw; G.bh = plan.bh; G.tiles_x = plan.tiles_x; G.tiles_y = plan.tiles_y;
     G.kchunks = P.w.cin_pad / 64;
     G.seg = g_seg_chunks;
+    G.k1 = P.a2.hi ? P.cin1 / 64 : 0;
     G.m_total = (long long)P.B * P.ho * P.wo;
     G.tiles_m = plan.flat ? cdiv(G.m_total, 128) : P.B * plan.tiles_x * plan.tiles_y;
     G.tiles_n = P.w.cout / plan.block_n;
