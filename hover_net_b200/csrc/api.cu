@@ -124,6 +124,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "branch_streams") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->branch_streams = (int)value; }
     else if (k == "tc_seg_chunks") tc_set_seg_chunks((int)value);
     else if (k == "tc_block_n") tc_set_block_n((int)value);
+    else if (k == "tc_res_tma") tc_set_res_tma((int)value);
     else if (k == "profile") { c->profile = (int)value; if (c->model) c->model->profile_ops = value >= 3 ? 2 : (value >= 2 ? 1 : 0); }
     else throw Error(HVN_ERR_INVALID, "unknown option " + k);
     API_END

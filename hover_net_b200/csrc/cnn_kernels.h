@@ -37,10 +37,12 @@ struct TcPlan {
     int tiles_x = 0, tiles_y = 0;
     int block_n = 0;
     int flat = 0;                // 1x1 stride-1 dense view: M flattened over B*H*W
+    int res_tma = 0;             // residual tile fetched by TMA (tmap_a2_hi holds its fp32 map)
 };
 bool tc_plan(const ConvParams &P, TcPlan &plan);
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s);
 void tc_set_block_n(int n);      // tuning knobs (0 = automatic)
 void tc_set_seg_chunks(int n);
+void tc_set_res_tma(int on);
 
 }  // namespace hvn

@@ -119,7 +119,10 @@ constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 
 template <int BLOCK_N> __host__ __device__ constexpr int tc_stage_bytes() { return 2 * A_TILE_BYTES + 2 * BLOCK_N * 128; }
 
-template <int BLOCK_N, int STAGES, int MODE, bool XF>
+// RT (residual mode, BLOCK_N = 64): the fp32 residual tile [128 px][64 ch] is fetched by TMA into a
+// two-slot shared-memory ring one tile ahead (tm_a2_hi carries its tensor map), instead of by
+// per-thread global loads -- the thin residual layers are bound by how many bytes an SM keeps in flight.
+template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false>
 __global__ void __launch_bounds__(TC_THREADS + (XF ? XF_WARPS * 32 : 0), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -149,7 +152,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
-        if (XF) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), XF_WARPS); }
+        if (XF || RT) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), XF ? XF_WARPS : EP_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -170,6 +173,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it_global = 0;
+            int tile_count = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int tm = tile / G.tiles_n, tn = tile - tm * G.tiles_n;
                 int n_img = 0, y0 = 0, x0 = 0;
@@ -181,6 +185,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     const int r = tm - n_img * per_img;
                     y0 = (r / G.tiles_x) * G.bh;
                     x0 = (r - (r / G.tiles_x) * G.tiles_x) * G.bw;
+                }
+                if constexpr (RT) {  // residual tile of this output tile -> ring slot (flat 2-D map [channels, pixels])
+                    const int r = tile_count & 1;
+                    const uint32_t rph = (uint32_t)(tile_count >> 1) & 1u;
+                    mbar_wait(rempty_bar(r), rph ^ 1u);
+                    mbar_expect_tx(rfull_bar(r), RAW_TILE_BYTES);
+                    tma_2d(raw_base + r * RAW_TILE_BYTES, &tm_a2_hi, rfull_bar(r), tn * BLOCK_N, (int)m0);
+                    ++tile_count;
                 }
                 for (int it = 0; it < kiters; ++it, ++it_global) {
                     if constexpr (XF) {  // raw fp32 A tile of this K-slice -> staging ring (tm_a_hi is the fp32 map)
@@ -318,6 +330,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         const int cb = half * CW;
         float *ep_tile = reinterpret_cast<float *>(smem_raw + (ep_base - smem_u32(smem_raw))) + (warp - 2) * 32 * 32;
         int scount = 0;
+        int tcount_e = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int tm = tile / G.tiles_n, tn = tile - tm * G.tiles_n;
             bool valid;
@@ -343,8 +356,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             // waited for, so their HBM latency hides behind the main loop.
             const int sub_px = lane >> 3, sub_g = lane & 7;
             constexpr int NCH = CW / 32;
-            float4 rpre[MODE == EPI_RES ? NCH : 1][MODE == EPI_RES ? 8 : 1];
-            if constexpr (MODE == EPI_RES) {
+            constexpr bool REG_RES = MODE == EPI_RES && !RT;
+            float4 rpre[REG_RES ? NCH : 1][REG_RES ? 8 : 1];
+            if constexpr (REG_RES) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int src = it * 4 + sub_px;
@@ -387,6 +401,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             // blocks through its private (XOR-swizzled) shared-memory tile so that 8 lanes cover the 32
             // channels of one pixel: 128 B of fp32 / 64 B of fp16 contiguous per pixel per instruction.
             // Skip loads (upsample mode) of 4 pixels-per-lane are issued before any of them is consumed.
+            const float *res_tile = nullptr;
+            if constexpr (RT) {
+                const int r = tcount_e & 1;
+                mbar_wait(rfull_bar(r), (uint32_t)(tcount_e >> 1) & 1u);
+                res_tile = reinterpret_cast<const float *>(smem_raw + (raw_base + r * RAW_TILE_BYTES - smem_u32(smem_raw)));
+            }
 #pragma unroll
             for (int c0 = 0; c0 < CW; c0 += 32) {
 #pragma unroll
@@ -407,7 +427,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         pn[u] = __shfl_sync(0xffffffffu, n_img, src);
                         py[u] = __shfl_sync(0xffffffffu, oy, src);
                         px[u] = __shfl_sync(0xffffffffu, ox, src);
-                        if constexpr (MODE == EPI_RES) pre[u].r = rpre[c0 / 32][bt * PB + u];
+                        if constexpr (RT) pre[u].r = *reinterpret_cast<const float4 *>(res_tile + (quad * 32 + src) * BLOCK_N + cb + c0 + sub_g * 4);
+                        else if constexpr (MODE == EPI_RES) pre[u].r = rpre[c0 / 32][bt * PB + u];
                         else if (pv[u]) epi_prefetch<MODE>(P, pn[u], py[u], px[u], ch, pre[u]);
                     }
 #pragma unroll
@@ -421,6 +442,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     }
                 }
                 __syncwarp();
+            }
+            if constexpr (RT) {  // this warp is done with the residual slot
+                if (lane == 0) mbar_arrive(rempty_bar(tcount_e & 1));
+                ++tcount_e;
             }
         }
         }
@@ -468,6 +493,8 @@ static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *d
 
 static int g_force_block_n = 0;
 static int g_seg_chunks = 4;  // 64-channel slices per accumulation segment (4 -> 48 chained MMAs)
+static int g_res_tma = 1, g_res_tma_max_chunks = 4;  // residual tile via TMA for 1x1 layers with K <= 256 (larger K: A re-reads of N=64 tiles cost more)
+void tc_set_res_tma(int on) { g_res_tma = on; }
 void tc_set_block_n(int n) { g_force_block_n = n; }
 void tc_set_seg_chunks(int n) { g_seg_chunks = n < 1 ? 1 : n; }
 
@@ -506,6 +533,17 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     }
     if (xf && bn != 128 && bn != 64) return false;
     cuuint32_t ones[4] = {1, 1, 1, 1};
+    plan.res_tma = 0;
+    if (P.res.p && !P.up2 && !two && !xf && plan.flat && g_res_tma && w.cout % 64 == 0 && w.cin_pad / 64 <= g_res_tma_max_chunks) {
+        const RawRef &r = P.res;
+        const bool dense_r = (long long)r.sW * r.w == r.sH && (long long)r.sH * r.h == r.sN && r.h == P.ho && r.w == P.wo;
+        if (dense_r && !(reinterpret_cast<uintptr_t>(r.p) & 15) && r.sW % 4 == 0) {
+            cuuint64_t rdims[2] = {(cuuint64_t)w.cout, (cuuint64_t)((long long)P.B * r.h * r.w)};
+            cuuint64_t rstr[1] = {(cuuint64_t)r.sW * 4};
+            cuuint32_t rbox[2] = {64, 128};
+            if (encode(plan.tmap_a2_hi, r.p, 2, rdims, rstr, rbox, ones, true)) { plan.res_tma = 1; bn = 64; plan.block_n = 64; }
+        }
+    }
     if (plan.flat) {
         cuuint64_t dims[2] = {(cuuint64_t)P.a.c, (cuuint64_t)((long long)P.B * P.a.h * P.a.w)};
         cuuint64_t str[1] = {(cuuint64_t)P.a.sW * 2};
@@ -574,14 +612,14 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     return true;
 }
 
-template <int BLOCK_N, int STAGES, int MODE, bool XF>
+template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false>
 static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 48 + EP_WARPS * 32 * 32 * 4 + 1024 +
-                         (XF ? 1024 + 2 * 128 * 64 * 4 : 0);
+                         ((XF || RT) ? 1024 + 2 * 128 * 64 * 4 : 0);
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr = false;
     if (!attr) {
-        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES, MODE, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES, MODE, XF, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     static int sms = 0;
@@ -595,7 +633,7 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
     memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
     memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
     memcpy(&a2_hi, plan.tmap_a2_hi, 128); memcpy(&a2_lo, plan.tmap_a2_lo, 128);
-    k_conv_tc<BLOCK_N, STAGES, MODE, XF><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
+    k_conv_tc<BLOCK_N, STAGES, MODE, XF, RT><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
 }
 
 template <int BLOCK_N, int STAGES>
@@ -609,7 +647,10 @@ static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, c
         throw Error(-1, "conv_tc: transformed input with unsupported tile shape");
     }
     if (P.up2) launch_tm<BLOCK_N, STAGES, EPI_UP2, false>(P, plan, G, s);
-    else if (P.res.p) launch_tm<BLOCK_N, STAGES, EPI_RES, false>(P, plan, G, s);
+    else if (P.res.p) {
+        if constexpr (BLOCK_N == 64) { if (plan.res_tma) { launch_tm<64, 2, EPI_RES, false, true>(P, plan, G, s); return; } }
+        launch_tm<BLOCK_N, STAGES, EPI_RES, false>(P, plan, G, s);
+    }
     else launch_tm<BLOCK_N, STAGES, EPI_PLAIN, false>(P, plan, G, s);
 }
 
