@@ -119,6 +119,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     if (k == "conv_path") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->conv_path = (int)value; }
     else if (k == "chunk") c->chunk = (int)value;
     else if (k == "flood_impl") postproc_set_flood_impl((int)value);
+    else if (k == "fuse_up2") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->fuse_up2 = (int)value; }
     else if (k == "fuse_shortcut") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->fuse_shortcut = (int)value; }
     else if (k == "xform") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->xform = (int)value; }
     else if (k == "branch_streams") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->branch_streams = (int)value; }

@@ -377,7 +377,7 @@ Plan &Model::plan(int B, int H, int W) {
     HVN_CHECK(finalized, -5, "weights not finalised (call hvn_finalize_weights)");
     HVN_CHECK(H == W, -1, "only square patches are supported (reference patch geometry is square)");
     std::string key = std::to_string(B) + "x" + std::to_string(H) + "x" + std::to_string(W) + "p" + std::to_string(conv_path) +
-                      "b" + std::to_string(branch_streams) + "x" + std::to_string(xform) + "f" + std::to_string(fuse_shortcut);
+                      "b" + std::to_string(branch_streams) + "x" + std::to_string(xform) + "f" + std::to_string(fuse_shortcut) + "u" + std::to_string(fuse_up2);
     auto it = plans_.find(key);
     if (it != plans_.end()) return *it->second;
     std::unique_ptr<Plan> pl(new Plan());
@@ -427,6 +427,14 @@ Plan &Model::plan(int B, int H, int W) {
         op.kind = Op::BNRELU;
         op.name = bnp;
         op.bn_in = in; op.bn_out = out; op.bn = bn_.at(bnp);
+        P.ops.push_back(op);
+    };
+    auto add_up2 = [&](const std::string &name, const RawRef &in, const SplitRef &skip, const SplitRef &out) {
+        Op op;
+        op.stream = cur_stream;
+        op.kind = Op::UP2ADD;
+        op.name = name + "+up2add";
+        op.up_in = in; op.up_skip = skip; op.up_out = out;
         P.ops.push_back(op);
     };
     auto tf_same_lo = [](int size, int ksize, int stride) {  // net_utils.py:51-63
@@ -498,9 +506,13 @@ Plan &Model::plan(int B, int H, int W) {
     };
     // ---- bottleneck: conv_bot, upsample x2, + d2
     SplitRef U3in = new_split(2 * ds[3], 2 * ds[3], 1024);
-    {
+    if (fuse_up2) {
         Op &op = add_conv("conv_bot.weight", D[3], 1, 0, ds[3], ds[3]);
         op.cp.up2 = 1; op.cp.skip = crop_to(D[2], 2 * ds[3]); op.cp.out_split = U3in;
+    } else {
+        RawRef Rb = new_raw(ds[3], ds[3], 1024);
+        { Op &op = add_conv("conv_bot.weight", D[3], 1, 0, ds[3], ds[3]); op.cp.out_raw = Rb; }
+        add_up2("conv_bot", Rb, crop_to(D[2], 2 * ds[3]), U3in);
     }
     // ---- decoder
     const int km1 = k - 1;
@@ -509,19 +521,21 @@ Plan &Model::plan(int B, int H, int W) {
     const int ho = 2 * w4;
     HVN_CHECK(ho == P.oh, -1, "internal: output size mismatch");
     const int nsets = branch_streams ? (int)branches_.size() : 1;  // private scratch per concurrent branch
-    RawRef C3[3], C2[3];
+    RawRef C3[3], C2[3], RS[3];
     SplitRef T3[3], T2[3], B3[3], B2[3], U2in[3], U1in[3];
     for (int i = 0; i < nsets; ++i) {
         C3[i] = new_raw(h3, h3, 512); C2[i] = new_raw(h2, h2, 256);
         T3[i] = new_split(h3, h3, 512); T2[i] = new_split(h2, h2, 256);
         B3[i] = new_split(h3, h3, 128); B2[i] = new_split(h2, h2, 128);
         U2in[i] = new_split(2 * w8, 2 * w8, 512); U1in[i] = new_split(ho, ho, 256);
+        if (!fuse_up2) RS[i] = new_raw(1, 1, std::max(w8 * w8 * 512, w4 * w4 * 256));  // convf output before up2+add
     }
     SplitRef Hf[3];
     for (size_t b = 0; b < branches_.size(); ++b) Hf[b] = new_split(ho, ho, 64);
 
     auto dense = [&](const std::string &pfx, const SplitRef &uin, const RawRef &Cb, const SplitRef &Tb,
-                     const SplitRef &Bb, int hin, int c0, int units, const SplitRef &skip, const SplitRef &out) {
+                     const SplitRef &Bb, int hin, int c0, int units, const SplitRef &skip, const SplitRef &out,
+                     const RawRef &Rscratch) {
         int hh = hin - km1;  // after conva (valid)
         { Op &op = add_conv(pfx + "conva.weight", uin, 1, 0, hh, hh); op.cp.out_raw = rview(Cb, 0, 0, hh, hh, 0, c0); }
         int c = c0;
@@ -542,11 +556,14 @@ Plan &Model::plan(int B, int H, int W) {
         int wl = hh - units * km1, ol = units * km1 / 2;
         if (!use_xf) add_bnrelu(pfx + "dense.blk_bna.bn", rview(Cb, ol, ol, wl, wl, 0, c), sview(Tb, ol, ol, wl, wl, 0, c));
         Op &op = add_conv(pfx + "convf.weight", sview(Tb, ol, ol, wl, wl, 0, c), 1, 0, wl, wl);
-        op.cp.up2 = 1; op.cp.skip = skip; op.cp.out_split = out;
+        RawRef Rf;
+        if (fuse_up2) { op.cp.up2 = 1; op.cp.skip = skip; op.cp.out_split = out; }
+        else { Rf = rview(Rscratch, 0, 0, wl, wl, 0, c); Rf.sH = wl * c; Rf.sW = c; Rf.sN = (long long)wl * wl * c; op.cp.out_raw = Rf; }
         if (use_xf) {
             const BNParams &pb = bn_.at(pfx + "dense.blk_bna.bn");
             op.cp.a_raw = rview(Cb, ol, ol, wl, wl, 0, c); op.cp.in_scale = pb.scale; op.cp.in_shift = pb.shift;
         }
+        if (!fuse_up2) add_up2(pfx + "convf", Rf, skip, out);
     };
 
     Op head;
@@ -558,8 +575,8 @@ Plan &Model::plan(int B, int H, int W) {
         const int si_ = branch_streams ? (int)b : 0;
         cur_stream = si_;
         const size_t first_op = P.ops.size();
-        dense(bp + "u3.", U3in, C3[si_], T3[si_], B3[si_], 2 * ds[3], 256, 8, crop_to(D[1], 2 * w8), U2in[si_]);
-        dense(bp + "u2.", U2in[si_], C2[si_], T2[si_], B2[si_], 2 * w8, 128, 4, crop_to(D[0], ho), U1in[si_]);
+        dense(bp + "u3.", U3in, C3[si_], T3[si_], B3[si_], 2 * ds[3], 256, 8, crop_to(D[1], 2 * w8), U2in[si_], RS[si_]);
+        dense(bp + "u2.", U2in[si_], C2[si_], T2[si_], B2[si_], 2 * w8, 128, 4, crop_to(D[0], ho), U1in[si_], RS[si_]);
         { Op &op = add_conv(bp + "u1.conva.weight", U1in[si_], 1, km1 / 2, ho, ho); set_bn(op, bp + "u0.bn", Hf[b]); }
         if (b == 0) P.ops[first_op].fork_point = true;
         head.head.feat[b] = Hf[b];
@@ -585,7 +602,7 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
     HVN_CHECK(B >= 1, -1, "empty batch");
     int oh, ow, oc;
     out_shape(H, W, oh, ow, oc);
-    if (chunk <= 0) chunk = 16;
+    if (chunk <= 0) chunk = 32;  // sub-batch size: large enough to fill 148 persistent CTAs on the thin decoder layers
     if (!side_[0]) {
         for (auto &st : side_) HVN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         HVN_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
@@ -647,6 +664,10 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
             case Op::BNRELU:
                 launch_bnrelu(op.bn_in, bc, op.bn.scale, op.bn.shift, op.bn_out, s);
                 r.cls = "bnrelu";
+                break;
+            case Op::UP2ADD:
+                launch_up2_add(op.up_in, bc, op.up_skip, op.up_out, s);
+                r.cls = "bnrelu";  // elementwise class
                 break;
             case Op::HEAD: {
                 HeadParams hp = op.head;

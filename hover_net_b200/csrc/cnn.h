@@ -26,7 +26,7 @@ struct ParamSpec {
 struct BNParams { float *scale = nullptr, *shift = nullptr; int c = 0; };
 
 struct Op {
-    enum Kind { CONV0, CONV, BNRELU, HEAD } kind = CONV;
+    enum Kind { CONV0, CONV, BNRELU, HEAD, UP2ADD } kind = CONV;
     std::string name;
     ConvParams cp;          // CONV
     TcPlan tc;              // CONV: tensor-core plan (ok=false -> referee kernel)
@@ -36,6 +36,8 @@ struct Op {
     RawRef bn_in; SplitRef bn_out; BNParams bn;
     // HEAD
     HeadParams head;
+    // UP2ADD
+    RawRef up_in; SplitRef up_skip, up_out;
     double flops = 0;       // 2*MACs of the reference layer (algorithmic)
     int stream = 0;         // 0 = context stream; 1,2 = side streams (decoder branches run concurrently)
     bool fork_point = false; // side streams may start once everything before this op has been issued
@@ -61,6 +63,7 @@ class Model {
     std::map<std::string, int> index;
     std::map<std::string, std::vector<float>> host;
     bool finalized = false;
+    int fuse_up2 = 0;        // 1: 2x upsample + skip add inside the conv epilogue; 0: separate streaming pass (faster)
     int fuse_shortcut = 1;   // fold each residual group's 1x1 shortcut into unit 0's conv3 (one GEMM over [a2 | x])
     int xform = 1;           // fuse pre-activation BN+ReLU into the consuming 1x1 conv's A-operand load
     int branch_streams = 1;  // run the decoder branches on separate streams

@@ -26,6 +26,7 @@ void launch_conv0(const uint8_t *img, int B, int H, int W, int pad, const float 
 void launch_bnrelu(const RawRef &in, int B, const float *scale, const float *shift, const SplitRef &out,
                    cudaStream_t s);
 void launch_head(const HeadParams &P, cudaStream_t s);
+void launch_up2_add(const RawRef &in, int B, const SplitRef &skip, const SplitRef &out, cudaStream_t s);
 
 // tcgen05 path (conv_tc.cu).  tc_plan() decides eligibility and builds the TMA descriptors once per
 // (layer, buffer geometry); tc_launch() issues the kernel.

@@ -245,6 +245,41 @@ void launch_bnrelu(const RawRef &in, int B, const float *scale, const float *shi
 }
 
 // ------------------------------------------------------------------------------------------------
+// out(2y+dy, 2x+dx) = split( in(y,x) + skip(2y+dy, 2x+dx) ) : 2x nearest-neighbour upsample + skip add
+// (reference net_utils.py:284-294, net_desc.py:133-139) as a streaming pass over the OUTPUT pixels.
+__global__ void __launch_bounds__(256) k_up2_add(RawRef in, int B, SplitRef skip, SplitRef out) {
+    const int c8 = in.c / 8, oh = 2 * in.h, ow = 2 * in.w;
+    const long long total = (long long)B * oh * ow * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c8);
+        long long pix = i / c8;
+        const int X = (int)(pix % ow);
+        long long t = pix / ow;
+        const int Y = (int)(t % oh), n = (int)(t / oh);
+        const int c = cq * 8;
+        const float *ip = in.p + n * in.sN + (long long)(Y >> 1) * in.sH + (long long)(X >> 1) * in.sW + c;
+        const float4 v0 = *reinterpret_cast<const float4 *>(ip), v1 = *reinterpret_cast<const float4 *>(ip + 4);
+        const long long so = n * skip.sN + (long long)Y * skip.sH + (long long)X * skip.sW + c;
+        const uint4 sh = *reinterpret_cast<const uint4 *>(skip.hi + so), sl = *reinterpret_cast<const uint4 *>(skip.lo + so);
+        const __half *hh = reinterpret_cast<const __half *>(&sh), *ll = reinterpret_cast<const __half *>(&sl);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        __half oh8[8], ol8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split_f32(v[k] + join_f16(hh[k], ll[k]), oh8[k], ol8[k]);
+        const long long oo = n * out.sN + (long long)Y * out.sH + (long long)X * out.sW + c;
+        *reinterpret_cast<uint4 *>(out.hi + oo) = *reinterpret_cast<uint4 *>(oh8);
+        *reinterpret_cast<uint4 *>(out.lo + oo) = *reinterpret_cast<uint4 *>(ol8);
+    }
+}
+
+void launch_up2_add(const RawRef &in, int B, const SplitRef &skip, const SplitRef &out, cudaStream_t s) {
+    long long total = (long long)B * 4 * in.h * in.w * (in.c / 8);
+    int blocks = (int)std::min<long long>(cdiv(total, 256), 148 * 32);
+    k_up2_add<<<blocks, 256, 0, s>>>(in, B, skip, out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // heads.  feat[b] is the BN+ReLU'd 64-channel map of branch b (order tp?, np, hv).
 __global__ void __launch_bounds__(128) k_head(HeadParams P) {
     __shared__ float s_w[3][HVN_MAX_TYPES][64];
