@@ -84,6 +84,17 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def measured_traffic(kernel_class):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        k = t["kernels"].get("k_conv_tc" if kernel_class == "conv_tc" else "k_conv_ref")
+        return {"dram_bytes_per_launch": k["dram_bytes"] / k["launches"], "launches": k["launches"], "batch": t["batch"],
+                "source": "profiles/r1_traffic.json (" + t["command"] + ")"}
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -329,7 +340,7 @@ def run_ours(args):
                          "frac": ach / peak if peak else None, "peak_source": pk_kind + " bf16_tflops_sustained",
                          "algorithmic_gflop_per_launch": d["gflop"] / max(1, d["launches"]),
                          "avg_launch_ms": d["ms"] / max(1, d["launches"]), "launches_per_step": d["launches"],
-                         "traffic": None,
+                         "traffic": measured_traffic(dom),
                          "note": "algorithmic 2*MACs of the reference graph; the kernel issues 3 fp16 MMAs per "
                                  "product (hi*hi+hi*lo+lo*hi), so frac <= 1/3 by construction"},
             "kernel_classes": prof,

@@ -38,6 +38,29 @@ def launches(path):
     return tot, cnt
 
 
+def traffic(path):
+    """per kernel: launches, summed dram bytes and time of the SECOND (profiled) pass of tools/ncu_target.py"""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    rows = list(csv.DictReader(lines))
+    ids = sorted({int(r["ID"]) for r in rows})
+    half = ids[len(ids) // 2]  # launches of the warm-up pass come first
+    for r in rows:
+        if int(r["ID"]) < half:
+            continue
+        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("hvn::", "")
+        name = re.sub(r"<.*", "", name)
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        d = per.setdefault(name, {"ids": set(), "bytes": 0.0, "ms": 0.0})
+        d["ids"].add(r["ID"])
+        if r["Metric Name"].startswith("dram__bytes"):
+            d["bytes"] += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        else:
+            d["ms"] += v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1e-6)
+    return {k: {"launches": len(v["ids"]), "dram_bytes": v["bytes"], "ms_under_ncu": v["ms"]} for k, v in per.items()}
+
+
 def main(tag):
     out = ["# ncu summaries, round %s (B200, `--clock-control none`)" % tag, ""]
     lp = os.path.join(ROOT, "gpurun_out", "%s_launches.csv" % tag)
@@ -45,7 +68,7 @@ def main(tag):
         tot, cnt = launches(lp)
         T = sum(tot.values())
         out += ["## Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 "
-                "--warmup 1 --batch 16 --no-cpu-baseline`", "",
+                "--warmup 1 --batch 32 --no-cpu-baseline`", "",
                 "Per-launch times under ncu are serialised and cold-cache: read the SHARES. Total %.1f ms over %d launches "
                 "(warm-up step + timed step + e2e step + profile passes)." % (T, sum(cnt.values())), "",
                 "| kernel | launches | total ms | share |", "|---|---:|---:|---:|"]
@@ -61,6 +84,19 @@ def main(tag):
                 if k in d:
                     out.append("| %s | %s %s |" % (k, d[k][0], d[k][1]))
             out.append("")
+    tp = os.path.join(ROOT, "gpurun_out", "%s_dram_bytes.csv" % tag)
+    if os.path.exists(tp):
+        import json
+        tr = traffic(tp)
+        meta = {"command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
+                           "python tools/ncu_target.py 32", "batch": 32, "kernels": tr}
+        json.dump(meta, open(os.path.join(ROOT, "profiles", "%s_traffic.json" % tag), "w"), indent=1)
+        out += ["## DRAM traffic per kernel, one forward+post-proc pass at B=32 (chunk 32)", "",
+                "| kernel | launches | DRAM bytes (read+write) | per launch |", "|---|---:|---:|---:|"]
+        for k, v in sorted(tr.items(), key=lambda x: -x[1]["dram_bytes"])[:12]:
+            out.append("| `%s` | %d | %.3f GB | %.1f MB |" % (k, v["launches"], v["dram_bytes"] / 1e9,
+                                                          v["dram_bytes"] / 1e6 / max(1, v["launches"])))
+        out.append("")
     path = os.path.join(ROOT, "profiles", "%s_ncu_summary.md" % tag)
     open(path, "w").write("\n".join(out) + "\n")
     print(path)
