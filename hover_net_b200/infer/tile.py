@@ -56,6 +56,44 @@ def _stitch(patch_info, patch_data, src_shape):
     return np.ascontiguousarray(m[: src_shape[0], : src_shape[1]])
 
 
+def run_patches(padded, patch_info, win, run_step, batch_size):
+    """Per-patch network outputs [n,h,w,C] for every row of patch_info, in patch_info order.
+    Multi-GPU: rank r runs the contiguous shard `shard_range(n, r, world)`; shards are padded to equal
+    length and exchanged with one all_gather (NCCL on device tensors, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    from ..dist import shard_range
+
+    n = patch_info.shape[0]
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_range(n, rank, world)
+    outs = []
+    for b0 in range(lo, hi, batch_size):
+        pi = patch_info[b0 : min(b0 + batch_size, hi)]
+        batch = np.stack([padded[y : y + win, x : x + win] for y, x, _, _ in pi])
+        outs.append(np.asarray(run_step(batch)))
+    if world == 1:
+        return np.concatenate(outs, axis=0)
+    import torch
+    probe = outs[0] if outs else np.asarray(run_step(np.stack([padded[:win, :win]])))  # shape of one output
+    per = -(-n // world)
+    mine = np.zeros((per,) + probe.shape[1:], dtype=np.float32)
+    if outs:
+        cat = np.concatenate(outs, axis=0)
+        mine[: cat.shape[0]] = cat
+    backend = dist.get_backend()
+    t = torch.from_numpy(mine)
+    t = t.cuda() if backend == "nccl" else t
+    full = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(full, t)
+    full = full.cpu().numpy()
+    parts = []
+    for r in range(world):
+        l, h = shard_range(n, r, world)
+        parts.append(full[r * per : r * per + (h - l)])
+    return np.concatenate(parts, axis=0)
+
+
 def _overlay(image, inst_dict, draw_dot=False, type_colour=None, line_thickness=2):
     """Contours (and optional centroid dots) over the image -- the role of reference
     misc/viz_utils.py:94-125; per-instance colours are seeded instead of the reference's shuffled HSV."""
@@ -93,16 +131,16 @@ class InferManager(base.InferManager):
     """Run inference on tiles."""
 
     def infer_image(self, img):
-        """RGB uint8 [H,W,3] -> (pred_map [H,W,C] float32, pred_inst int32 [H,W], inst_info_dict)."""
+        """RGB uint8 [H,W,3] -> (pred_map [H,W,C] float32, pred_inst int32 [H,W], inst_info_dict).
+
+        With torch.distributed initialised (one process per GPU) the patches of the image are sharded
+        across the ranks and the per-patch maps gathered on every rank (`run_patches`); the single
+        whole-map post-processing -- its min/max normalisations are global -- then
+        runs on each rank's device identically."""
         src_shape = img.shape
         padded, patch_info, _ = _prepare_patching(img, self.patch_input_shape, self.patch_output_shape, True)
-        win = self.patch_input_shape
-        outs = []
-        for b0 in range(0, patch_info.shape[0], self.batch_size):
-            pi = patch_info[b0 : b0 + self.batch_size]
-            batch = np.stack([padded[y : y + win, x : x + win] for y, x, _, _ in pi])
-            outs.append(self.run_step(batch))
-        pred_map = _stitch(patch_info, np.concatenate(outs, axis=0), src_shape)
+        outs = run_patches(padded, patch_info, self.patch_input_shape, self.run_step, self.batch_size)
+        pred_map = _stitch(patch_info, outs, src_shape)
         pred_inst, inst_info_dict = self.post_proc_func(pred_map, nr_types=self.nr_types, return_centroids=True)
         return np.squeeze(pred_map), pred_inst, inst_info_dict
 

@@ -62,3 +62,41 @@ def test_gather_tables_gloo_world2():
     for i, r in enumerate(rows):
         assert len(r) == n_all[i]
         assert all(10000 * i <= v < 10000 * i + 1000 for row in r for v in row), "rows must stay in global tile order"
+
+
+def _tile_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hover_net_b200.infer import tile
+    img = np.random.default_rng(5).integers(0, 256, (500, 333, 3), dtype=np.uint8)
+    padded, pinfo, _ = tile._prepare_patching(img, 256, 164, True)
+
+    def fake_step(batch):  # a per-patch function of the patch content only
+        b = batch.astype(np.float32)
+        return np.stack([b[:, 46:210, 46:210, 0], b[:, 46:210, 46:210, 1], b[:, 46:210, 46:210, 2],
+                         b[:, 46:210, 46:210].sum(-1)], -1)
+
+    outs = tile.run_patches(padded, pinfo, 256, fake_step, 5)
+    m = tile._stitch(pinfo, outs, img.shape)
+    if rank == 0:
+        out.put(m)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tile_patches_sharded_gloo_world3_equals_single():
+    """config[3] plumbing: patches of one image sharded over 3 ranks, gathered, stitched == 1-rank result
+    (here the valid-conv crop of the padded image must reproduce the source image exactly)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tile_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    m = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    img = np.random.default_rng(5).integers(0, 256, (500, 333, 3), dtype=np.uint8).astype(np.float32)
+    assert m.shape == (500, 333, 4)
+    assert np.array_equal(m[..., :3], img) and np.array_equal(m[..., 3], img.sum(-1))

@@ -131,3 +131,37 @@ def test_config0_single_270_tile_original_seg_only():
         assert np.array_equal(info[k]["bbox"], oinfo[k]["bbox"]) and np.array_equal(info[k]["centroid"], oinfo[k]["centroid"])
         assert np.array_equal(info[k]["contour"], oinfo[k]["contour"]) and info[k]["type"] is None
     mgr.net.ctx.close()
+
+
+@pytest.mark.gpu
+def test_config3_4k_tile_single_gpu_properties():
+    """BASELINE configs[3] on one GPU: a 4096x4096 synthetic image through the tile driver (25x25 = 625
+    fast-mode patches, stitched 4100^2 -> 4096^2, ONE whole-map post-processing with its global min/max).
+    The CNN oracle cannot run 625 patches in a test; the map-level checks are size-independent:
+    oracle post-processing of the device-produced map is bit-identical, the run is reproducible, and
+    the instance table is consistent with inst_map."""
+    from hover_net_b200 import synth
+    from hover_net_b200.infer.tile import InferManager
+    from oracle import postproc_oracle as P
+
+    mode, nt = "fast", 6
+    base = synth.make_patches(4, 256, seed=90)
+    rng = np.random.default_rng(4)
+    rows = [np.concatenate([base[rng.integers(0, 4)] for _ in range(16)], 1) for _ in range(16)]
+    img = np.concatenate(rows, 0)
+    assert img.shape == (4096, 4096, 3)
+    sd = synth.make_state_dict(mode, nt, seed=0)
+    mgr = InferManager(method={"model_args": {"nr_types": nt, "mode": mode}, "model_path": sd}, type_info_path=None)
+    mgr.patch_input_shape, mgr.patch_output_shape, mgr.batch_size = 256, 164, 125
+    padded, pinfo, _ = tile._prepare_patching(img, 256, 164, True)
+    assert len(pinfo) == 625
+    pred_map, pred_inst, info = mgr.infer_image(img)
+    assert pred_map.shape == (4096, 4096, 4) and pred_inst.shape == (4096, 4096)
+    oi, otab = P.process_table(pred_map, nt)
+    assert np.array_equal(pred_inst, oi), "%d px differ" % int((pred_inst != oi).sum())
+    ids, counts = np.unique(pred_inst[pred_inst > 0], return_counts=True)
+    assert np.array_equal(ids, otab[:, 0]) and np.array_equal(counts, otab[:, 5])
+    assert set(info.keys()) <= set(int(i) for i in ids)  # dict drops only the <3-point contours
+    _, pred_inst2, _ = mgr.infer_image(img)
+    assert np.array_equal(pred_inst, pred_inst2)
+    mgr.net.ctx.close()
