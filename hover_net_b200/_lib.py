@@ -142,6 +142,44 @@ class Context:
             check(rc)
             return inst, table, nrows
 
+    def postproc_contours(self, pred, nr_types=None, max_rows=None, pts_cap=None):
+        """postproc + device contour tracing: (inst, table, nrows, offs [n*max_rows+1], pts [total,2])."""
+        p = np.ascontiguousarray(pred, dtype=np.float32)
+        if p.ndim == 3:
+            p = p[None]
+        n, H, W, C = p.shape
+        if max_rows is None:
+            max_rows = max(16, H * W // 64)
+        if pts_cap is None:
+            pts_cap = max(4096, n * H * W // 16)
+        while True:
+            inst = np.empty((n, H, W), dtype=np.int32)
+            table = np.zeros((n, max_rows, ROW_LEN), dtype=np.int64)
+            nrows = np.zeros((n,), dtype=np.int32)
+            offs = np.zeros((n * max_rows + 1,), dtype=np.int32)
+            pts = np.empty((pts_cap, 2), dtype=np.int32)
+            L = lib()
+            L.hvn_postproc_contours.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+            rc = L.hvn_postproc_contours(self._h, _ptr(p), n, H, W, C, int(nr_types or 0), _ptr(inst), _ptr(table),
+                                         int(max_rows), _ptr(nrows), _ptr(pts), int(pts_cap), _ptr(offs))
+            if rc == -4:  # HVN_ERR_CAPACITY: the table or the point buffer was too small -- retry with exact sizes
+                if int(nrows.max()) > max_rows:
+                    max_rows = int(nrows.max())
+                else:
+                    pts_cap = int(offs[-1])
+                continue
+            check(rc)
+            return inst, table, nrows, offs, pts[: int(offs[-1])]
+
+    def contours_dev(self, d_inst, d_table, d_nrows, n, H, W, max_rows, d_pts, pts_cap, d_offs):
+        L = lib()
+        L.hvn_contours_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        check(L.hvn_contours_dev(self._h, _ptr(d_inst), _ptr(d_table), _ptr(d_nrows), n, H, W, int(max_rows), _ptr(d_pts),
+                                 int(pts_cap), _ptr(d_offs)))
+
     def forward_postproc(self, imgs_u8, want_pred=True, max_rows=None):
         x = np.ascontiguousarray(imgs_u8, dtype=np.uint8)
         B, H, W, _ = x.shape

@@ -16,6 +16,7 @@ SOURCES = [
     ("conv_ref.cu", []),
     ("conv_tc.cu", []),
     ("postproc.cu", ["-fmad=false"]),
+    ("contour.cu", []),
 ]
 
 

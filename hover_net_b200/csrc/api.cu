@@ -126,6 +126,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "tc_seg_chunks") tc_set_seg_chunks((int)value);
     else if (k == "tc_block_n") tc_set_block_n((int)value);
     else if (k == "tc_res_tma") tc_set_res_tma((int)value);
+    else if (k == "tc_halo") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->tc_halo = (int)value; }
     else if (k == "profile") { c->profile = (int)value; if (c->model) c->model->profile_ops = value >= 3 ? 2 : (value >= 2 ? 1 : 0); }
     else throw Error(HVN_ERR_INVALID, "unknown option " + k);
     API_END
@@ -253,6 +254,54 @@ int hvn_postproc(hvn_ctx *c, const float *pred, int n, int H, int W, int C, int 
     HVN_CUDA(cudaStreamSynchronize(c->stream));
     finish_profile(c, false, true);
     check_rows(n_rows, n, max_rows);
+    API_END
+}
+
+int hvn_contours_dev(hvn_ctx *c, const int32_t *inst, const int64_t *table, const int32_t *n_rows, int n, int H, int W,
+                     int max_rows, int32_t *pts, int64_t cap, int32_t *offs) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(inst && table && n_rows && offs && (pts || cap == 0), HVN_ERR_INVALID, "null buffer");
+    HVN_CHECK(n >= 1 && H >= 1 && W >= 1 && max_rows >= 1 && cap >= 0, HVN_ERR_INVALID, "bad shape");
+    HVN_CHECK((long long)n * max_rows < (1ll << 31), HVN_ERR_INVALID, "too many table rows");
+    c->pp_launches += contours_run(c->stream, inst, (const long long *)table, n_rows, n, H, W, max_rows, pts, cap, offs);
+    API_END
+}
+
+int hvn_postproc_contours(hvn_ctx *c, const float *pred, int n, int H, int W, int C, int nr_types, int32_t *inst,
+                          int64_t *table, int max_rows, int32_t *n_rows, int32_t *pts, int64_t cap, int32_t *offs) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(pred && inst && table && n_rows && offs && (pts || cap == 0), HVN_ERR_INVALID, "null buffer");
+    HVN_CHECK(n >= 1 && H >= 1 && W >= 1 && cap >= 0, HVN_ERR_INVALID, "empty input");
+    HVN_CHECK((long long)n * max_rows < (1ll << 31), HVN_ERR_INVALID, "too many table rows");
+    size_t px = (size_t)n * H * W;
+    size_t tb = (size_t)n * max_rows * HVN_ROW_LEN;
+    size_t no = (size_t)n * max_rows + 1;
+    c->io_arena.reset();
+    c->io_arena.reserve(px * C * 4 + px * 4 + tb * 8 + (size_t)n * 4 + no * 4 + (size_t)cap * 8 + 8192);
+    float *d_pred = c->io_arena.take<float>(px * C);
+    int32_t *d_inst = c->io_arena.take<int32_t>(px);
+    int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    int32_t *d_nr = c->io_arena.take<int32_t>(n);
+    int32_t *d_offs = c->io_arena.take<int32_t>(no);
+    int32_t *d_pts = c->io_arena.take<int32_t>((size_t)cap * 2 + 2);
+    HVN_CUDA(cudaMemcpyAsync(d_pred, pred, px * C * 4, cudaMemcpyHostToDevice, c->stream));
+    run_postproc(c, d_pred, n, H, W, C, nr_types, d_inst, d_tab, max_rows, d_nr);
+    c->pp_launches += contours_run(c->stream, d_inst, (const long long *)d_tab, d_nr, n, H, W, max_rows, d_pts, cap, d_offs);
+    HVN_CUDA(cudaMemcpyAsync(inst, d_inst, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(n_rows, d_nr, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(table, d_tab, tb * 8, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(offs, d_offs, no * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    finish_profile(c, false, true);
+    check_rows(n_rows, n, max_rows);
+    const long long total = offs[no - 1];
+    HVN_CHECK(total <= cap, HVN_ERR_CAPACITY, "contour buffer too small: " + std::to_string(total) + " points, pts_cap=" + std::to_string(cap));
+    if (total > 0) {
+        HVN_CUDA(cudaMemcpyAsync(pts, d_pts, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+        HVN_CUDA(cudaStreamSynchronize(c->stream));
+    }
     API_END
 }
 

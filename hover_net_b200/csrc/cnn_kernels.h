@@ -39,11 +39,14 @@ struct TcPlan {
     int block_n = 0;
     int flat = 0;                // 1x1 stride-1 dense view: M flattened over B*H*W
     int res_tma = 0;             // residual tile fetched by TMA (tmap_a2_hi holds its fp32 map)
+    int halo = 0;                // k x k stride-1 layer served from one halo tile per 64-channel block
+    int halo_w = 0, halo_h = 0;  // halo extent in pixels (bw + kw - 1, bh + kh - 1)
 };
 bool tc_plan(const ConvParams &P, TcPlan &plan);
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s);
 void tc_set_block_n(int n);      // tuning knobs (0 = automatic)
 void tc_set_seg_chunks(int n);
 void tc_set_res_tma(int on);
+void tc_set_halo(int mode);      // 0 off, 1 auto (thin k x k layers), 2 every eligible layer
 
 }  // namespace hvn

@@ -24,6 +24,14 @@
 //   extra "transform" warps build the A tiles themselves -- coalesced fp32 loads, y=relu(x*scale+shift),
 //   fp16 hi/lo split, 128B-swizzled st.shared, fence.proxy.async -- so the pre-activated copy of the
 //   tensor never exists in HBM (no separate BN/ReLU pass, no second output of the producing layer).
+// * HALO variant (k x k stride-1 layers): the old path re-fetches the A tile once per filter tap, which
+//   makes thin layers (cout 32/64) L2->SM bandwidth bound (~6300 B/clk chip-wide).  Here ONE halo tile
+//   ((16+kh-1) x (8+kw-1) pixels x 64 channels, hi and lo) is fetched per 64-channel block and every tap's
+//   MMA reads its shifted 16x8 window straight out of it: the A descriptor starts (ky*Wp + kx) rows into the
+//   halo and steps SBO = Wp*128 B between 8-pixel rows.  tcgen05.mma resolves the 128B swizzle from absolute
+//   shared-memory address bits (tools/umma_shift_probe.cu, measured on B200: any 128 B-row start offset and
+//   any SBO multiple of 128 B reads what TMA wrote), so no re-layout is needed.  Weights stream through their
+//   own ring, one (tap, 64-channel) tile per stage.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -96,11 +104,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;   // SWIZZLE_128B
     return d;
@@ -110,6 +118,9 @@ struct TcGeom {
     int flat, bw, bh, tiles_x, tiles_y, tiles_m, tiles_n, kchunks, seg;
     int k1;  // > 0: K-slices [0,k1) come from the first source, [k1,kchunks) from the second (fused shortcut)
     long long m_total;
+    // HALO variant: halo tile of halo_w x halo_h pixels per 64-channel block, a_plane bytes per fp16 plane
+    // (1024-aligned), na slots (1 or 2)
+    int halo_w, halo_h, a_plane, na;
 };
 
 constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
@@ -122,14 +133,15 @@ template <int BLOCK_N> __host__ __device__ constexpr int tc_stage_bytes() { retu
 // RT (residual mode, BLOCK_N = 64): the fp32 residual tile [128 px][64 ch] is fetched by TMA into a
 // two-slot shared-memory ring one tile ahead (tm_a2_hi carries its tensor map), instead of by
 // per-thread global loads -- the thin residual layers are bound by how many bytes an SM keeps in flight.
-template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false>
+template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false, bool HALO = false>
 __global__ void __launch_bounds__(TC_THREADS + (XF ? XF_WARPS * 32 : 0), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
           const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
           const ConvParams P, const TcGeom G) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int STAGE_BYTES = tc_stage_bytes<BLOCK_N>();
+    // HALO: the ring holds weight tiles only; the halo slots live where XF/RT keep their staging ring
+    constexpr int STAGE_BYTES = HALO ? 2 * BLOCK_N * 128 : tc_stage_bytes<BLOCK_N>();
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
     // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base pointer
@@ -153,6 +165,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
         if (XF || RT) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), XF ? XF_WARPS : EP_WARPS); }
+        if (HALO) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), 1); }  // halo slots: full / empty
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -172,6 +185,49 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+          if constexpr (HALO) {
+            // Blocks = (tile, 64-channel slice) pairs in execution order.  The halo of block b+1 is requested
+            // while block b's weight tiles stream, so its latency hides behind a block's worth of MMAs.
+            const uint32_t halo_tx = (uint32_t)(2 * G.halo_w * G.halo_h * 128);
+            auto issue_halo = [&](int tile, int kc, int ablk) {
+                const int tm = tile / G.tiles_n;
+                const int per_img = G.tiles_x * G.tiles_y;
+                const int n_img = tm / per_img;
+                const int r = tm - n_img * per_img;
+                const int y0 = (r / G.tiles_x) * G.bh, x0 = (r - (r / G.tiles_x) * G.tiles_x) * G.bw;
+                const int slot = ablk % G.na;
+                const uint32_t ph = (uint32_t)(ablk / G.na) & 1u;
+                mbar_wait(rempty_bar(slot), ph ^ 1u);
+                mbar_expect_tx(rfull_bar(slot), halo_tx);
+                const uint32_t dst = raw_base + (uint32_t)(slot * 2 * G.a_plane);
+                tma_4d(dst, &tm_a_hi, rfull_bar(slot), kc * 64, x0 - P.pad_l, y0 - P.pad_t, n_img);
+                tma_4d(dst + (uint32_t)G.a_plane, &tm_a_lo, rfull_bar(slot), kc * 64, x0 - P.pad_l, y0 - P.pad_t, n_img);
+            };
+            int ablk = 0, wit = 0;
+            // After this tap's weights the next halo is requested.  Two slots: as soon as the ring has wrapped
+            // once (the previous block is then complete); one slot: only after ALL of this block's weights are
+            // in flight -- the request waits for this block's MMAs, which need those weights.
+            const int t_next = G.na >= 2 ? (taps < STAGES ? taps : STAGES) - 1 : taps - 1;
+            if ((int)blockIdx.x < total_tiles) issue_halo(blockIdx.x, 0, 0);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int tn = tile - (tile / G.tiles_n) * G.tiles_n;
+                for (int kc = 0; kc < G.kchunks; ++kc, ++ablk) {
+                    for (int tap = 0; tap < taps; ++tap, ++wit) {
+                        const int s = wit % STAGES;
+                        const uint32_t ph = (uint32_t)(wit / STAGES) & 1u;
+                        mbar_wait(empty_bar(s), ph ^ 1u);
+                        const uint32_t b_hi = smem_base + s * STAGE_BYTES, b_lo = b_hi + BLOCK_N * 128;
+                        mbar_expect_tx(full_bar(s), (uint32_t)(2 * BLOCK_N * 128));
+                        tma_3d(b_hi, &tm_w_hi, full_bar(s), kc * 64, tn * BLOCK_N, tap);
+                        tma_3d(b_lo, &tm_w_lo, full_bar(s), kc * 64, tn * BLOCK_N, tap);
+                        if (tap == t_next) {
+                            if (kc + 1 < G.kchunks) issue_halo(tile, kc + 1, ablk + 1);
+                            else if (tile + (int)gridDim.x < total_tiles) issue_halo(tile + gridDim.x, 0, ablk + 1);
+                        }
+                    }
+                }
+            }
+          } else {
             int it_global = 0;
             int tile_count = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -235,12 +291,53 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     tma_3d(b_lo, &tm_w_lo, full_bar(s), kc * 64, tn * BLOCK_N, tap);
                 }
             }
+          }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+          if constexpr (HALO) {
+            // it = kc * taps + tap (channel-slice major): all taps of a slice read the same halo slot
+            const uint32_t sbo = (uint32_t)G.halo_w * 128u;
+            int ablk = 0, wit = 0, scount = 0, slot = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
+                    const int as = scount & 1;
+                    const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
+                    mbar_wait(tempty_bar(as), aph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                    const int it1 = min(it0 + G.seg, kiters);
+                    for (int it = it0; it < it1; ++it, ++wit) {
+                        const int kc = it / taps, tap = it - kc * taps;
+                        if (tap == 0) {
+                            slot = ablk % G.na;
+                            mbar_wait(rfull_bar(slot), (uint32_t)(ablk / G.na) & 1u);
+                        }
+                        const int s = wit % STAGES;
+                        mbar_wait(full_bar(s), (uint32_t)(wit / STAGES) & 1u);
+                        tc_fence_after();
+                        const int ky = tap / P.w.kw, kx = tap - ky * P.w.kw;
+                        const uint32_t a0 = raw_base + (uint32_t)(slot * 2 * G.a_plane) + (uint32_t)((ky * G.halo_w + kx) * 128);
+                        const uint32_t sb = smem_base + s * STAGE_BYTES;
+                        const uint64_t da_hi = umma_desc(a0, sbo), da_lo = umma_desc(a0 + (uint32_t)G.a_plane, sbo),
+                                       db_hi = umma_desc(sb), db_lo = umma_desc(sb + BLOCK_N * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
+                        }
+                        tc_commit(empty_bar(s));
+                        if (tap == taps - 1) { tc_commit(rempty_bar(slot)); ++ablk; }  // halo slot reusable
+                    }
+                    tc_commit(tfull_bar(as));
+                }
+            }
+          } else {
             int it_global = 0, scount = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
@@ -271,6 +368,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     tc_commit(tfull_bar(as));     // segment complete -> epilogue warps drain it
                 }
             }
+          }
         }
     } else if (XF && warp >= 2 + EP_WARPS) {
         // ===================== A-operand transform (warps 10..13, XF only) =====================
@@ -494,6 +592,8 @@ static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *d
 static int g_force_block_n = 0;
 static int g_seg_chunks = 4;  // 64-channel slices per accumulation segment (4 -> 48 chained MMAs)
 static int g_res_tma = 1, g_res_tma_max_chunks = 4;  // residual tile via TMA for 1x1 layers with K <= 256 (larger K: A re-reads of N=64 tiles cost more)
+static int g_halo = 1;  // 0 off, 1 auto (thin k x k layers: cout tile <= 64, or >= 25 taps), 2 every eligible layer
+void tc_set_halo(int mode) { g_halo = mode; }
 void tc_set_res_tma(int on) { g_res_tma = on; }
 void tc_set_block_n(int n) { g_force_block_n = n; }
 void tc_set_seg_chunks(int n) { g_seg_chunks = n < 1 ? 1 : n; }
@@ -544,6 +644,19 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
             if (encode(plan.tmap_a2_hi, r.p, 2, rdims, rstr, rbox, ones, true)) { plan.res_tma = 1; bn = 64; plan.block_n = 64; }
         }
     }
+    plan.halo = 0;
+    if (g_halo && w.taps > 1 && P.stride == 1 && !xf && !two && !P.up2 && !P.res.p && w.kh <= 5 && w.kw <= 5 &&
+        (g_halo >= 2 || bn <= 64 || w.taps >= 25)) {
+        plan.halo = 1;
+        plan.bw = 8; plan.bh = 16;   // one 8-pixel row per swizzle group, 16 rows = the 128 accumulator rows
+        plan.halo_w = plan.bw + w.kw - 1; plan.halo_h = plan.bh + w.kh - 1;
+        plan.tiles_x = cdiv(P.wo, plan.bw); plan.tiles_y = cdiv(P.ho, plan.bh);
+        cuuint64_t dims[4] = {(cuuint64_t)P.a.c, (cuuint64_t)P.a.w, (cuuint64_t)P.a.h, (cuuint64_t)P.B};
+        cuuint64_t str[3] = {(cuuint64_t)P.a.sW * 2, (cuuint64_t)P.a.sH * 2, (cuuint64_t)P.a.sN * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)plan.halo_w, (cuuint32_t)plan.halo_h, 1};
+        if (!encode(plan.tmap_a_hi, P.a.hi, 4, dims, str, box, ones)) return false;
+        if (!encode(plan.tmap_a_lo, P.a.lo, 4, dims, str, box, ones)) return false;
+    } else
     if (plan.flat) {
         cuuint64_t dims[2] = {(cuuint64_t)P.a.c, (cuuint64_t)((long long)P.B * P.a.h * P.a.w)};
         cuuint64_t str[1] = {(cuuint64_t)P.a.sW * 2};
@@ -636,6 +749,39 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
     k_conv_tc<BLOCK_N, STAGES, MODE, XF, RT><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
 }
 
+constexpr int SMEM_LIMIT = 232448;
+template <int BLOCK_N, int STAGES> constexpr int halo_fixed_smem() {
+    return STAGES * 2 * BLOCK_N * 128 + 8 * (2 * STAGES + 4) + 48 + EP_WARPS * 32 * 32 * 4 + 1024 + 1024;
+}
+
+// HALO variant: weight ring of STAGES tiles + `na` halo slots (two fp16 planes each) behind the epilogue tiles.
+template <int BLOCK_N, int STAGES>
+static bool launch_halo(const ConvParams &P, const TcPlan &plan, TcGeom G, cudaStream_t s, int min_na) {
+    constexpr int fixed = halo_fixed_smem<BLOCK_N, STAGES>();
+    const int slot = 2 * G.a_plane;
+    G.na = fixed + 2 * slot <= SMEM_LIMIT ? 2 : (fixed + slot <= SMEM_LIMIT ? 1 : 0);
+    if (G.na < min_na) return false;
+    const int smem = fixed + G.na * slot;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_tc<BLOCK_N, STAGES, EPI_PLAIN, false, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int grid = std::min(G.tiles_m * G.tiles_n, sms);
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
+    memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
+    k_conv_tc<BLOCK_N, STAGES, EPI_PLAIN, false, false, true><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, a_hi, a_lo, P, G);
+    return true;
+}
+
 template <int BLOCK_N, int STAGES>
 static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     if (P.in_scale) {  // transformed input: only the shapes the plan produces (1x1, plain or upsample epilogue)
@@ -663,6 +809,18 @@ void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     G.m_total = (long long)P.B * P.ho * P.wo;
     G.tiles_m = plan.flat ? cdiv(G.m_total, 128) : P.B * plan.tiles_x * plan.tiles_y;
     G.tiles_n = P.w.cout / plan.block_n;
+    G.halo_w = plan.halo_w; G.halo_h = plan.halo_h; G.na = 0;
+    G.a_plane = (plan.halo_w * plan.halo_h * 128 + 1023) & ~1023;
+    if (plan.halo) {
+        bool ok = false;
+        switch (plan.block_n) {
+        case 128: ok = launch_halo<128, 3>(P, plan, G, s, 1); break;
+        case 64: ok = launch_halo<64, 6>(P, plan, G, s, 2) || launch_halo<64, 4>(P, plan, G, s, 1); break;
+        default: ok = launch_halo<32, 8>(P, plan, G, s, 1); break;
+        }
+        if (!ok) throw Error(-1, "conv_tc: halo tile does not fit shared memory");
+        return;
+    }
     switch (plan.block_n) {
     case 128: launch_t<128, 3>(P, plan, G, s); break;
     case 64: launch_t<64, 4>(P, plan, G, s); break;

@@ -26,4 +26,10 @@ size_t postproc_workspace_bytes(int n, int H, int W, int nr_types);
 int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, int H, int W, int C, int nr_types,
                  int *inst, long long *table, int max_rows, int *n_rows, std::string *prof = nullptr);
 
+// Contours of every table row (contour.cu): offs [n*max_rows + 1] i32 exclusive prefix of the per-row point
+// counts, pts [cap][2] i32 (x, y) in map coordinates.  All pointers are device pointers.  Returns the number
+// of kernels launched.
+int contours_run(cudaStream_t stream, const int *inst, const long long *table, const int *n_rows, int n_maps, int H,
+                 int W, int max_rows, int *pts, long long cap, int *offs);
+
 }  // namespace hvn

@@ -2,9 +2,10 @@
 
 Module-level and picklable like the reference's (it is shipped to pool workers under `spawn`,
 infer/tile.py:353-363); each process lazily opens its own post-processing context on
-`HVN_DEVICE` / `LOCAL_RANK` / device 0.  Contours come from cv2.findContours on the bbox crop of
-the device-produced inst_map exactly as the reference does (:133-143) -- host work per instance,
-SURVEY.md row f3."""
+`HVN_DEVICE` / `LOCAL_RANK` / device 0.  Contours are traced on the device (csrc/contour.cu, SURVEY.md
+row f3): point for point the reference's cv2.findContours(..., RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0] on the
+bbox crop (:133-143); centroids come from the instance table's exact integer sums, evaluated in the
+reference's float order (m10/m00 + cmin, :144-152).  No per-instance image work is left on the host."""
 import os
 
 import numpy as np
@@ -22,27 +23,20 @@ def _ctx():
     return _CTX[key]
 
 
-def table_to_dict(inst, table, nr_types):
-    """Instance table rows -> the reference's inst_info_dict (post_proc.py:120-181)."""
-    import cv2
-
+def table_to_dict(table, offs, pts, nr_types):
+    """Instance table rows + device-traced contours -> the reference's inst_info_dict (post_proc.py:120-181).
+    table [n,10], offs [>= n+1] (point range of row r = pts[offs[r]:offs[r+1]]), pts [total,2] (x, y)."""
     info = {}
-    for r in table:
+    for k, r in enumerate(table):
         iid, rmin, cmin, rmax, cmax, area, sx, sy, tp, tc = (int(v) for v in r)
-        crop = (inst[rmin:rmax, cmin:cmax] == iid).astype(np.uint8)
-        cnt = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
-        cnt = np.squeeze(cnt[0][0].astype("int32"))
-        if cnt.shape[0] < 3:  # < 3 points dont make a contour (:140-141)
+        cnt = pts[int(offs[k]) : int(offs[k + 1])]
+        if cnt.shape[0] < 3:  # < 3 points dont make a contour (:140-143; a 1-point contour squeezes to 1-D there)
             continue
-        if len(cnt.shape) != 2:
-            continue
-        m = cv2.moments(crop)  # the reference's exact float path for the centroid (== sum/area)
-        cen = np.array([m["m10"] / m["m00"], m["m01"] / m["m00"]])
-        cnt[:, 0] += cmin
-        cnt[:, 1] += rmin
+        # cv2.moments of the bbox crop: m00 = area, m10 = sum(x - cmin), m01 = sum(y - rmin) -- exact integers
+        cen = np.array([float(sx - cmin * area) / float(area), float(sy - rmin * area) / float(area)])
         cen[0] += cmin
         cen[1] += rmin
-        info[iid] = {"bbox": np.array([[rmin, cmin], [rmax, cmax]]), "centroid": cen, "contour": cnt,
+        info[iid] = {"bbox": np.array([[rmin, cmin], [rmax, cmax]]), "centroid": cen, "contour": np.array(cnt, dtype=np.int32),
                      "type_prob": None, "type": None}
         if nr_types is not None:
             info[iid]["type"] = int(tp)
@@ -59,9 +53,9 @@ def process(pred_map, nr_types=None, return_centroids=False):
             raise ValueError("typed post-processing expects [tp, np, hv_x, hv_y] channels")
     elif pm.shape[-1] != 3:
         raise ValueError("seg-only post-processing expects [np, hv_x, hv_y] channels")
-    inst, table, nrows = _ctx().postproc(pm.astype(np.float32, copy=False), nr_types)
-    inst = inst[0]
-    info = None
-    if return_centroids or nr_types is not None:
-        info = table_to_dict(inst, table[0, : int(nrows[0])], nr_types)
-    return inst, info
+    if not (return_centroids or nr_types is not None):
+        inst, table, nrows = _ctx().postproc(pm.astype(np.float32, copy=False), nr_types)
+        return inst[0], None
+    inst, table, nrows, offs, pts = _ctx().postproc_contours(pm.astype(np.float32, copy=False), nr_types)
+    info = table_to_dict(table[0, : int(nrows[0])], offs, pts, nr_types)
+    return inst[0], info

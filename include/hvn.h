@@ -70,7 +70,7 @@ int hvn_finalize_weights(hvn_ctx *ctx);
  *                      "profile" = 0 | 1 | 2 (see hvn_stage_ms). */
 int hvn_set_option(hvn_ctx *ctx, const char *key, int64_t value);
 const char *hvn_debug_log(const hvn_ctx *ctx);
-/* counters: "kernel_launches", "tc_launches", "pp_launches", "last_flops" (algorithmic 2*MACs of the
+/* counters: "kernel_launches", "tc_launches", "pp_launches" (post-processing and contour kernels), "last_flops" (algorithmic 2*MACs of the
  * last forward); with option "profile" = 2 also "launches:<class>" and "flops:<class>" for
  * class in {conv_tc, conv_ref, conv0, bnrelu, head} (see hvn_stage_ms). */
 int64_t hvn_get_counter(const hvn_ctx *ctx, const char *key);
@@ -92,6 +92,19 @@ int hvn_postproc(hvn_ctx *ctx, const float *pred_host, int n_maps, int H, int W,
                  int32_t *inst_host, int64_t *table_host, int max_rows, int32_t *n_rows_host);
 int hvn_postproc_dev(hvn_ctx *ctx, const float *pred_dev, int n_maps, int H, int W, int C, int nr_types,
                      int32_t *inst_dev, int64_t *table_dev, int max_rows, int32_t *n_rows_dev);
+
+/* ---- per-instance contours (post_proc.py:133-147): for every table row the outer border of the instance,
+ * point for point cv2.findContours(inst_map[rmin:rmax, cmin:cmax] == id, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0]
+ * plus the (cmin, rmin) offset, traced on the device.  offs [n_maps*max_rows + 1] int32: the points of row r
+ * of map m are pts[offs[m*max_rows + r] : offs[m*max_rows + r + 1]] (rows past n_rows[m] are empty);
+ * pts [pts_cap,2] int32 (x, y).  HVN_ERR_CAPACITY when offs[n_maps*max_rows] > pts_cap (offs is valid then,
+ * no points are written for rows that do not fit).  The caller applies the reference's "< 3 points" drop rule
+ * (:140-141).  hvn_postproc_contours = hvn_postproc + contours with one round trip of the maps. */
+int hvn_contours_dev(hvn_ctx *ctx, const int32_t *inst_dev, const int64_t *table_dev, const int32_t *n_rows_dev,
+                     int n_maps, int H, int W, int max_rows, int32_t *pts_dev, int64_t pts_cap, int32_t *offs_dev);
+int hvn_postproc_contours(hvn_ctx *ctx, const float *pred_host, int n_maps, int H, int W, int C, int nr_types,
+                          int32_t *inst_host, int64_t *table_host, int max_rows, int32_t *n_rows_host,
+                          int32_t *pts_host, int64_t pts_cap, int32_t *offs_host);
 
 /* ---- fused tile path: infer_step then process on every patch, pred map stays in HBM.
  * pred_host / pred_dev may be NULL when the caller does not want the float maps back. */

@@ -432,3 +432,60 @@ API int hvo_process(const float *pred_map, int H, int W, int C, int nr_types, in
     free(acc); free(tcnt);
     return rows;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Contour of one instance: the first contour of cv2.findContours(crop, RETR_TREE, CHAIN_APPROX_SIMPLE)
+ * on the bbox crop `inst[rmin:rmax, cmin:cmax] == id` (reference post_proc.py:133-137), plus the bbox
+ * offset (:146-147).  Restates OpenCV's Suzuki-Abe border following (modules/imgproc/src/contours.cpp,
+ * icvFetchContour; 4.x `contours_new.cpp` yields the same sequence -- pinned against cv2 4.13 in
+ * tests/test_oracle_contour.py): start at the first pixel in raster order, direction codes
+ * 0..7 = E,NE,N,NW,W,SW,S,SE, the previous pixel is the first non-zero neighbour clockwise from NW,
+ * each step searches counter-clockwise from the previous pixel, and CHAIN_APPROX_SIMPLE keeps a point
+ * only where the step direction changes.  An instance is one 8-connected component (flood regions are
+ * 4-connected), so the first contour IS this outer border.
+ * Returns the number of points (x, y pairs written to pts up to cap points). */
+static const int HVO_DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+static const int HVO_DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+API int hvo_contour(const int32_t *inst, int H, int W, int32_t id, int rmin, int cmin, int rmax, int cmax,
+                    int32_t *pts, int cap)
+{
+    (void)H;
+#define F(y, x) ((y) >= rmin && (y) < rmax && (x) >= cmin && (x) < cmax && inst[(size_t)(y) * W + (x)] == id)
+    int y0 = -1, x0 = -1;
+    for (int y = rmin; y < rmax && y0 < 0; ++y)
+        for (int x = cmin; x < cmax; ++x)
+            if (inst[(size_t)y * W + x] == id) { y0 = y; x0 = x; break; }
+    if (y0 < 0) return 0;
+    int n = 0;
+    int s_end = 4, s = 4;
+    do {
+        s = (s - 1) & 7;
+        if (F(y0 + HVO_DY[s], x0 + HVO_DX[s])) break;
+    } while (s != s_end);
+    if (s == s_end) { /* isolated pixel */
+        if (n < cap) { pts[0] = x0; pts[1] = y0; }
+        return 1;
+    }
+    const int y1 = y0 + HVO_DY[s], x1 = x0 + HVO_DX[s];
+    int y3 = y0, x3 = x0, prev_s = s ^ 4;
+    for (;;) {
+        int y4, x4;
+        for (;;) {
+            ++s;
+            y4 = y3 + HVO_DY[s & 7]; x4 = x3 + HVO_DX[s & 7];
+            if (F(y4, x4)) break;
+        }
+        s &= 7;
+        if (s != prev_s) {
+            if (n < cap) { pts[2 * n] = x3; pts[2 * n + 1] = y3; }
+            ++n;
+            prev_s = s;
+        }
+        if (y4 == y0 && x4 == x0 && y3 == y1 && x3 == x1) break;
+        y3 = y4; x3 = x4;
+        s = (s + 4) & 7;
+    }
+#undef F
+    return n;
+}

@@ -129,6 +129,17 @@ def process_table(pred_map, nr_types=None):
     return inst, table[:n].copy()
 
 
+def contour(inst, iid, rmin, cmin, rmax, cmax, cap=4096):
+    """[n,2] int32 (x, y) in map coordinates: the oracle's restatement of
+    cv2.findContours(crop, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0] + (cmin, rmin)."""
+    a = np.ascontiguousarray(inst, dtype=np.int32)
+    pts = np.empty((cap, 2), dtype=np.int32)
+    lib().hvo_contour.restype = ctypes.c_int
+    n = lib().hvo_contour(_p(a), a.shape[0], a.shape[1], int(iid), int(rmin), int(cmin), int(rmax), int(cmax), _p(pts), cap)
+    assert 0 <= n <= cap
+    return pts[:n].copy()
+
+
 def process(pred_map, nr_types=None, return_centroids=False):
     """Reference-shaped result: (pred_inst, inst_info_dict or None)  -- post_proc.py:94-186."""
     import cv2

@@ -104,3 +104,64 @@ def test_three_flood_implementations_agree(ctx, oracle_pp):
             _check(ctx, oracle_pp, maps, None)
     finally:
         ctx.set_option("flood_impl", 0)
+
+
+def _cv2_contour(inst, row):
+    import cv2
+    iid, rmin, cmin, rmax, cmax = (int(v) for v in row[:5])
+    c = cv2.findContours((inst[rmin:rmax, cmin:cmax] == iid).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+    return c[0][0].reshape(-1, 2).astype(np.int32) + np.array([cmin, rmin], np.int32)
+
+
+@pytest.mark.parametrize("hw,nt,n", [((164, 164), 6, 6), ((80, 80), None, 4), ((97, 133), 5, 3), ((512, 512), None, 1)])
+def test_device_contours_equal_cv2_findcontours(ctx, hw, nt, n):
+    """Row f3: every instance's device-traced contour == the reference's cv2.findContours call
+    (post_proc.py:133-137), point for point, on nuclei maps and on irregular smooth-field blobs."""
+    import cv2
+    rng = np.random.default_rng(21)
+    maps = [synth.synth_pred_map(hw[0], hw[1], nt, s) for s in range(n)]
+    if nt is None:  # irregular blobs with holes and thin necks
+        m = np.stack([cv2.GaussianBlur(rng.standard_normal(hw), (0, 0), s) for s in (5, 3, 3)], -1)
+        m = m / np.abs(m).max((0, 1))
+        m[..., 0] = 0.55 + 0.5 * m[..., 0]
+        maps.append(m.astype(np.float32))
+    maps = np.stack(maps)
+    inst, table, nrows, offs, pts = ctx.postproc_contours(maps, nt)
+    i2, t2, n2 = ctx.postproc(maps, nt)
+    assert np.array_equal(inst, i2) and np.array_equal(table, t2) and np.array_equal(nrows, n2)
+    max_rows = table.shape[1]
+    assert offs[0] == 0 and offs[-1] == len(pts) and np.all(np.diff(offs) >= 0)
+    total = 0
+    for m in range(maps.shape[0]):
+        for r in range(int(nrows[m])):
+            k = m * max_rows + r
+            got = pts[offs[k] : offs[k + 1]]
+            assert np.array_equal(got, _cv2_contour(inst[m], table[m, r])), (m, r)
+            total += 1
+        assert offs[m * max_rows + int(nrows[m])] == offs[(m + 1) * max_rows]  # rows past n_rows are empty
+    assert total > 10
+
+
+def test_device_contours_small_buffer_reports_capacity(ctx):
+    from hover_net_b200 import _lib
+    maps = np.stack([synth.synth_pred_map(164, 164, 6, 0)])
+    inst, table, nrows, offs, pts = ctx.postproc_contours(maps, 6, pts_cap=8)  # retried internally with the exact size
+    assert len(pts) == offs[-1] > 8
+    full = ctx.postproc_contours(maps, 6)
+    assert np.array_equal(pts, full[4]) and np.array_equal(offs, full[3])
+    _ = _lib
+
+
+def test_process_contours_match_oracle_process(oracle_pp):
+    """`process` (device contours + table centroids) == the oracle's `process` (cv2.findContours / cv2.moments)."""
+    from hover_net_b200.models.hovernet.post_proc import process
+    for nt, seed in ((6, 3), (None, 4)):
+        pm = synth.synth_pred_map(164, 164, nt, seed)
+        inst, info = process(pm, nr_types=nt, return_centroids=True)
+        oi, oinfo = oracle_pp.process(pm, nr_types=nt, return_centroids=True)
+        assert np.array_equal(inst, oi) and sorted(info.keys()) == sorted(oinfo.keys())
+        for k in info:
+            assert np.array_equal(info[k]["contour"], oinfo[k]["contour"]) and info[k]["contour"].dtype == np.int32
+            assert np.array_equal(info[k]["centroid"], oinfo[k]["centroid"])
+            assert np.array_equal(info[k]["bbox"], oinfo[k]["bbox"])
+            assert info[k]["type"] == oinfo[k]["type"] and info[k]["type_prob"] == oinfo[k]["type_prob"]

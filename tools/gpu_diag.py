@@ -49,6 +49,12 @@ if __name__ == "__main__":
     if "cnn" in what: cnn()
 
 
+def _knobs(net):
+    """development knobs from the environment: HVN_TC_HALO=0|1|2"""
+    if os.environ.get("HVN_TC_HALO"):
+        net.ctx.set_option("tc_halo", int(os.environ["HVN_TC_HALO"]))
+
+
 def tc(mode="fast", nt=6, verbose=False):
     """per-layer tcgen05-vs-referee self test (conv_path=2), then the end-to-end check"""
     import re
@@ -58,6 +64,7 @@ def tc(mode="fast", nt=6, verbose=False):
     x = synth.make_patches(int(g["batch"]), arch.PATCH_GEOMETRY[mode][0], seed=7)
     net = create_model(mode=mode, nr_types=nt)
     net.load_state_dict(synth.make_state_dict(mode, nt, 0))
+    _knobs(net)
     for seg in (4,):
         net.ctx.set_option("tc_seg_chunks", seg)
         net.ctx.set_option("conv_path", 2)
@@ -71,7 +78,9 @@ def tc(mode="fast", nt=6, verbose=False):
         rows.sort(reverse=True)
         if verbose:
             print("\n".join(log))
-        print("seg=%d: worst layers by relative diff:" % seg)
+        halo_rows = [r for r in rows if "H bn=" in r[1]]
+        print("seg=%d: %d layers, %d on the halo variant (worst halo rel %.2e); worst layers by relative diff:" % (
+            seg, len(rows), len(halo_rows), max([r[0] for r in halo_rows] or [0.0])))
         for rel, ln in rows[:4]:
             print("   rel %.2e | %s" % (rel, ln[:150]))
         d = np.abs(out[..., -3:] - g["out"][..., -3:])
@@ -98,6 +107,7 @@ def layers(mode="fast", B=8):
     x = synth.make_patches(B, arch.PATCH_GEOMETRY[mode][0], seed=7)
     net = create_model(mode=mode, nr_types=nt)
     net.load_state_dict(synth.make_state_dict(mode, nt, 0))
+    _knobs(net)
     net.ctx.set_option("chunk", B)
     net.ctx.set_option("branch_streams", 0)
     net.ctx.forward(x)
