@@ -180,6 +180,52 @@ class Context:
         check(L.hvn_contours_dev(self._h, _ptr(d_inst), _ptr(d_table), _ptr(d_nrows), n, H, W, int(max_rows), _ptr(d_pts),
                                  int(pts_cap), _ptr(d_offs)))
 
+    def tile_grid(self, H, W, patch_in):
+        r, c = ctypes.c_int(), ctypes.c_int()
+        check(lib().hvn_tile_grid(self._h, int(H), int(W), int(patch_in), ctypes.byref(r), ctypes.byref(c)))
+        return r.value, c.value
+
+    def infer_tile(self, img_u8, patch_in, batch=0, want_pred=True, contours=True, max_rows=None, pts_cap=None):
+        """One RGB image [H,W,3] through the device tile path (reflect pad, patches, network, stitch, crop,
+        process, contours).  Returns (pred or None, inst, table [n,10], offs or None, pts or None)."""
+        x = np.ascontiguousarray(img_u8, dtype=np.uint8)
+        H, W, C = x.shape
+        assert C == 3
+        _, _, oc = self.out_shape(patch_in, patch_in)
+        if max_rows is None:
+            max_rows = max(16, H * W // 64)
+        if pts_cap is None:
+            pts_cap = max(4096, H * W // 16)
+        L = lib()
+        L.hvn_infer_tile.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        while True:
+            pred = np.empty((H, W, oc), dtype=np.float32) if want_pred else None
+            inst = np.empty((H, W), dtype=np.int32)
+            table = np.zeros((max_rows, ROW_LEN), dtype=np.int64)
+            nrows = np.zeros((1,), dtype=np.int32)
+            offs = np.zeros((max_rows + 1,), dtype=np.int32) if contours else None
+            pts = np.empty((pts_cap, 2), dtype=np.int32) if contours else None
+            rc = L.hvn_infer_tile(self._h, _ptr(x), H, W, int(patch_in), int(batch), _ptr(pred), _ptr(inst), _ptr(table),
+                                  int(max_rows), _ptr(nrows), _ptr(pts), int(pts_cap if contours else 0), _ptr(offs))
+            if rc == -4:
+                if int(nrows[0]) > max_rows:
+                    max_rows = int(nrows[0])
+                else:
+                    pts_cap = int(offs[-1])
+                continue
+            check(rc)
+            n = int(nrows[0])
+            return pred, inst, table[:n], offs, (pts[: int(offs[-1])] if contours else None)
+
+    def tile_predict_dev(self, d_img, H, W, patch_in, cell_lo, cell_hi, batch, d_pred):
+        L = lib()
+        L.hvn_tile_predict_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        check(L.hvn_tile_predict_dev(self._h, _ptr(d_img), int(H), int(W), int(patch_in), int(cell_lo), int(cell_hi),
+                                     int(batch), _ptr(d_pred)))
+
     def forward_postproc(self, imgs_u8, want_pred=True, max_rows=None):
         x = np.ascontiguousarray(imgs_u8, dtype=np.uint8)
         B, H, W, _ = x.shape

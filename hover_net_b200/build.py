@@ -17,6 +17,7 @@ SOURCES = [
     ("conv_tc.cu", []),
     ("postproc.cu", ["-fmad=false"]),
     ("contour.cu", []),
+    ("tile.cu", []),
 ]
 
 

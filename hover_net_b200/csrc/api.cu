@@ -6,6 +6,7 @@
 #include "../../include/hvn.h"
 #include "cnn.h"
 #include "postproc.h"
+#include "tile.h"
 
 using namespace hvn;
 
@@ -17,6 +18,7 @@ struct hvn_ctx {
     std::unique_ptr<Model> model;  // null for post-processing-only contexts
     Arena pp_arena;                // post-processing workspace
     Arena io_arena;                // staging for the host-pointer entry points
+    Arena tile_arena;              // patch / output batches of the tile path
     int chunk = 0;
     int profile = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -76,6 +78,7 @@ void hvn_destroy(hvn_ctx *c) {
     c->model.reset();
     c->pp_arena.release();
     c->io_arena.release();
+    c->tile_arena.release();
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &e : c->tev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -351,6 +354,85 @@ int hvn_forward_postproc(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, f
     HVN_CUDA(cudaStreamSynchronize(c->stream));
     finish_profile(c, true, true);
     check_rows(n_rows, B, max_rows);
+    API_END
+}
+
+// ---------------------------------------------------------------------------------------------------
+int hvn_tile_grid(const hvn_ctx *c, int H, int W, int patch_in, int *rows, int *cols) {
+    API_BEGIN
+    HVN_CHECK(c && c->model, HVN_ERR_STATE, "context has no model");
+    HVN_CHECK(H >= 1 && W >= 1 && rows && cols, HVN_ERR_INVALID, "bad argument");
+    int oh, ow, oc;
+    c->model->out_shape(patch_in, patch_in, oh, ow, oc);
+    tile_grid(H, W, oh, rows, cols);
+    API_END
+}
+
+static int run_tile_predict(hvn_ctx *c, const uint8_t *img, int H, int W, int patch_in, int lo, int hi, int batch, float *pred) {
+    int oh, ow, oc;
+    c->model->out_shape(patch_in, patch_in, oh, ow, oc);
+    if (batch < 1) batch = 64;
+    c->tile_arena.reset();
+    c->tile_arena.reserve(tile_workspace_bytes(patch_in, oh, oc, batch) + 1024);
+    return tile_predict(*c->model, c->tile_arena, c->stream, img, H, W, patch_in, lo, hi, batch, c->chunk, pred);
+}
+
+int hvn_tile_predict_dev(hvn_ctx *c, const uint8_t *img, int H, int W, int patch_in, int cell_lo, int cell_hi, int batch,
+                         float *pred) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    HVN_CHECK(img && pred && H >= 1 && W >= 1, HVN_ERR_INVALID, "bad argument");
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    c->model->kernel_launches += run_tile_predict(c, img, H, W, patch_in, cell_lo, cell_hi, batch, pred);
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    finish_profile(c, true, false);
+    API_END
+}
+
+int hvn_infer_tile(hvn_ctx *c, const uint8_t *img, int H, int W, int patch_in, int batch, float *pred, int32_t *inst,
+                   int64_t *table, int max_rows, int32_t *n_rows, int32_t *pts, int64_t cap, int32_t *offs) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+    HVN_CHECK(img && inst && table && n_rows && H >= 1 && W >= 1 && max_rows >= 1, HVN_ERR_INVALID, "bad argument");
+    HVN_CHECK(!offs || pts || cap == 0, HVN_ERR_INVALID, "contours requested without a point buffer");
+    int oh, ow, oc, rows, cols;
+    c->model->out_shape(patch_in, patch_in, oh, ow, oc);
+    tile_grid(H, W, oh, &rows, &cols);
+    const size_t px = (size_t)H * W, tb = (size_t)max_rows * HVN_ROW_LEN, no = (size_t)max_rows + 1;
+    if (!offs) cap = 0;
+    c->io_arena.reset();
+    c->io_arena.reserve(px * 3 + px * oc * 4 + px * 4 + tb * 8 + no * 4 + (size_t)cap * 8 + 16384);
+    uint8_t *d_img = c->io_arena.take<uint8_t>(px * 3);
+    float *d_pred = c->io_arena.take<float>(px * oc);
+    int32_t *d_inst = c->io_arena.take<int32_t>(px);
+    int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    int32_t *d_nr = c->io_arena.take<int32_t>(1);
+    int32_t *d_offs = c->io_arena.take<int32_t>(no);
+    int32_t *d_pts = c->io_arena.take<int32_t>((size_t)cap * 2 + 2);
+    HVN_CUDA(cudaMemcpyAsync(d_img, img, px * 3, cudaMemcpyHostToDevice, c->stream));
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    c->model->kernel_launches += run_tile_predict(c, d_img, H, W, patch_in, 0, rows * cols, batch, d_pred);
+    if (c->profile) HVN_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    run_postproc(c, d_pred, 1, H, W, oc, c->model->nr_types, d_inst, d_tab, max_rows, d_nr);
+    if (offs) c->pp_launches += contours_run(c->stream, d_inst, (const long long *)d_tab, d_nr, 1, H, W, max_rows, d_pts, cap, d_offs);
+    if (pred) HVN_CUDA(cudaMemcpyAsync(pred, d_pred, px * oc * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(inst, d_inst, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(n_rows, d_nr, 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaMemcpyAsync(table, d_tab, tb * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (offs) HVN_CUDA(cudaMemcpyAsync(offs, d_offs, no * 4, cudaMemcpyDeviceToHost, c->stream));
+    HVN_CUDA(cudaStreamSynchronize(c->stream));
+    finish_profile(c, true, true);
+    check_rows(n_rows, 1, max_rows);
+    if (offs) {
+        const long long total = offs[no - 1];
+        HVN_CHECK(total <= cap, HVN_ERR_CAPACITY, "contour buffer too small: " + std::to_string(total) + " points, pts_cap=" + std::to_string(cap));
+        if (total > 0) {
+            HVN_CUDA(cudaMemcpyAsync(pts, d_pts, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+            HVN_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
     API_END
 }
 

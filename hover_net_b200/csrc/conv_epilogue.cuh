@@ -14,6 +14,20 @@ __device__ __forceinline__ void split_f32(float x, __half &hi, __half &lo) {
 
 __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
 
+// Four values at once with the packed conversions (one F2FP per pair): same roundings as split_f32.
+// NONNEG: the inputs are already >= 0 (post-ReLU), so only the upper clamp is needed.
+template <bool NONNEG = false>
+__device__ __forceinline__ void split4_f32(const float t[4], uint2 &hi, uint2 &lo) {
+    float x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = NONNEG ? fminf(t[i], 65504.f) : fminf(fmaxf(t[i], -65504.f), 65504.f);
+    const __half2 h01 = __floats2half2_rn(x[0], x[1]), h23 = __floats2half2_rn(x[2], x[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(x[0] - f01.x, x[1] - f01.y), l23 = __floats2half2_rn(x[2] - f23.x, x[3] - f23.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+}
+
 // 4 consecutive output channels c..c+3 of output pixel (n, oy, ox); c % 4 == 0.
 __device__ __forceinline__ void conv_epilogue4(const ConvParams &P, int n, int oy, int ox, int c, float v[4]) {
     if (P.res.p) {
@@ -89,11 +103,10 @@ __device__ __forceinline__ void epi_prefetch(const ConvParams &P, int n, int oy,
 }
 
 __device__ __forceinline__ void store_split4(const SplitRef &o, long long off, const float t[4]) {
-    __half oh[4], ol[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i]);
-    *reinterpret_cast<uint2 *>(o.hi + off) = *reinterpret_cast<uint2 *>(oh);
-    *reinterpret_cast<uint2 *>(o.lo + off) = *reinterpret_cast<uint2 *>(ol);
+    uint2 oh, ol;
+    split4_f32(t, oh, ol);
+    *reinterpret_cast<uint2 *>(o.hi + off) = oh;
+    *reinterpret_cast<uint2 *>(o.lo + off) = ol;
 }
 
 template <int MODE>

@@ -9,8 +9,9 @@
 //   1x1 stride-1 convolutions over a dense buffer use a flat 2-D [pixels, channels] map instead.
 // * W tiles (BLOCK_N couts x 64 cin, hi and lo) come from the [tap][cout][cin] K-major weight tensor.
 // * Both operands land in 128B-swizzled shared memory; one elected thread issues
-//   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16) three times per K-slice:
-//   hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM  => fp32-grade products from fp16 tensor cores.
+//   tcgen05.mma.cta_group::1.kind::f16 (M=128, K=16) twice per K-slice: a_hi x [w_hi | w_lo] (N = 2*BLOCK_N,
+//   the two weight tiles are adjacent in shared memory) and a_lo x w_hi (N = BLOCK_N); the epilogue sums the
+//   halves: hi*hi + hi*lo + lo*hi, fp32 accumulation => fp32-grade products from fp16 tensor cores.
 // * Persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM
 //   allocator), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused BN/ReLU/residual/upsample ->
 //   global).  Shared-memory ring of STAGES operand slots; two TMEM accumulator buffers so the epilogue
@@ -159,7 +160,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    // two accumulation buffers of 2*BLOCK_N columns: [hi*hi + lo*hi | hi*lo] (see the MMA issuer)
+    constexpr uint32_t TMEM_COLS = 4 * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
@@ -298,6 +300,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // Measured on B200 (tools/umma_rate_probe.cu): an SS-mode M=128 K=16 MMA costs max(71.6, N/2) cycles --
+            // the 128x32 B A-operand read is a floor that N <= 128 never amortises.  The W hi and lo tiles are
+            // adjacent in shared memory, so ONE N = 2*BLOCK_N instruction computes a_hi*[w_hi | w_lo] into the two
+            // halves of the accumulation buffer, and a second N = BLOCK_N instruction adds a_lo*w_hi to the first
+            // half: 2 instructions per K-step instead of 3; the epilogue sums the halves in fp32 registers.
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
           if constexpr (HALO) {
             // it = kc * taps + tap (channel-slice major): all taps of a slice read the same halo slot
             const uint32_t sbo = (uint32_t)G.halo_w * 128u;
@@ -308,7 +316,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
                     mbar_wait(tempty_bar(as), aph ^ 1u);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BLOCK_N);
                     const int it1 = min(it0 + G.seg, kiters);
                     for (int it = it0; it < it1; ++it, ++wit) {
                         const int kc = it / taps, tap = it - kc * taps;
@@ -323,12 +331,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         const uint32_t a0 = raw_base + (uint32_t)(slot * 2 * G.a_plane) + (uint32_t)((ky * G.halo_w + kx) * 128);
                         const uint32_t sb = smem_base + s * STAGE_BYTES;
                         const uint64_t da_hi = umma_desc(a0, sbo), da_lo = umma_desc(a0 + (uint32_t)G.a_plane, sbo),
-                                       db_hi = umma_desc(sb), db_lo = umma_desc(sb + BLOCK_N * 128);
+                                       db_hi = umma_desc(sb);  // [w_hi | w_lo]: 2*BLOCK_N contiguous rows
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ko = (uint64_t)(2 * k);
-                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > it0 || k > 0) ? 1u : 0u);
-                            tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc2, (it > it0 || k > 0) ? 1u : 0u);
                             tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
                         }
                         tc_commit(empty_bar(s));
@@ -345,7 +352,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
                     mbar_wait(tempty_bar(as), aph ^ 1u);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BLOCK_N);
                     const int it1 = min(it0 + G.seg, kiters);
                     for (int it = it0; it < it1; ++it, ++it_global) {
                         const int s = it_global % STAGES;
@@ -354,13 +361,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         tc_fence_after();
                         const uint32_t sa = smem_base + s * STAGE_BYTES;
                         const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
-                                       db_hi = umma_desc(sa + 2 * A_TILE_BYTES),
-                                       db_lo = umma_desc(sa + 2 * A_TILE_BYTES + BLOCK_N * 128);
+                                       db_hi = umma_desc(sa + 2 * A_TILE_BYTES);  // [w_hi | w_lo]: 2*BLOCK_N contiguous rows
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {  // 4 x K=16 inside the 64-channel slice: +32 B per step
                             const uint64_t ko = (uint64_t)(2 * k);
-                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > it0 || k > 0) ? 1u : 0u);
-                            tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc2, (it > it0 || k > 0) ? 1u : 0u);
                             tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
                         }
                         tc_commit(empty_bar(s));  // slot reusable once these MMAs have read it
@@ -404,13 +409,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     float y4[4] = {fmaxf(v.x * sc.x + sh.x, 0.f), fmaxf(v.y * sc.y + sh.y, 0.f),
                                    fmaxf(v.z * sc.z + sh.z, 0.f), fmaxf(v.w * sc.w + sh.w, 0.f)};
                     if (!cok) y4[0] = y4[1] = y4[2] = y4[3] = 0.f;  // channels past cin (zero weights) must stay finite
-                    __half oh[4], ol[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) split_f32(y4[k], oh[k], ol[k]);
+                    uint2 oh, ol;
+                    split4_f32<true>(y4, oh, ol);
                     // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
                     const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
-                    *reinterpret_cast<uint2 *>(a_hi + off) = *reinterpret_cast<uint2 *>(oh);
-                    *reinterpret_cast<uint2 *>(a_lo + off) = *reinterpret_cast<uint2 *>(ol);
+                    *reinterpret_cast<uint2 *>(a_hi + off) = oh;
+                    *reinterpret_cast<uint2 *>(a_lo + off) = ol;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
@@ -482,11 +486,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
                 mbar_wait(tfull_bar(as), aph);
                 tc_fence_after();
-                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BLOCK_N + cb);
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BLOCK_N + cb);
 #pragma unroll
                 for (int c0 = 0; c0 < CW; c0 += 32) {
                     uint32_t r[32];
-                    tc_ld32(t_addr + (uint32_t)c0, r);
+                    tc_ld32(t_addr + (uint32_t)c0, r);                       // a_hi*w_hi + a_lo*w_hi
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+                    tc_ld32(t_addr + (uint32_t)(BLOCK_N + c0), r);           // a_hi*w_lo
                     tc_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);

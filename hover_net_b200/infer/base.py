@@ -50,6 +50,7 @@ class InferManager(object):
             state = torch.load(src, map_location="cpu")["desc"]
         net.load_state_dict(state, strict=True)  # strips an optional `module.` prefix itself
         self.net = net
+        self.device_tile_path = True  # infer/tile.py: pad / patch / stitch / crop / process on the device
         self.run_step = lambda input_batch: run_desc.infer_step(input_batch, net)
         self.post_proc_func = post_proc.process
         return

@@ -133,14 +133,40 @@ class InferManager(base.InferManager):
     def infer_image(self, img):
         """RGB uint8 [H,W,3] -> (pred_map [H,W,C] float32, pred_inst int32 [H,W], inst_info_dict).
 
-        With torch.distributed initialised (one process per GPU) the patches of the image are sharded
-        across the ranks and the per-patch maps gathered on every rank (`run_patches`); the single
-        whole-map post-processing -- its min/max normalisations are global -- then
-        runs on each rank's device identically."""
-        src_shape = img.shape
-        padded, patch_info, _ = _prepare_patching(img, self.patch_input_shape, self.patch_output_shape, True)
-        outs = run_patches(padded, patch_info, self.patch_input_shape, self.run_step, self.batch_size)
-        pred_map = _stitch(patch_info, outs, src_shape)
+        Device path (a manager built by `InferManager(**method_args)`): reflect padding, patch extraction,
+        stitching, cropping, `process` and the contours all run in libhvn (`hvn_infer_tile`); only the image
+        goes up and the maps / instance table / contour points come back.  With torch.distributed initialised
+        on NCCL (one process per GPU) each rank runs its contiguous slice of the patch grid into a zeroed
+        device map and the maps are summed with one all_reduce (disjoint supports: x + 0 is exact); the single
+        whole-map post-processing -- its min/max normalisations are global -- then runs on
+        every rank identically.  Host path (fake `run_step` in the CPU tests, gloo): `run_patches` + `_stitch`."""
+        import torch.distributed as dist
+        from ..dist import shard_range
+        from ..models.hovernet.post_proc import table_to_dict
+
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        win = int(self.patch_input_shape)
+        if getattr(self, "device_tile_path", False) and (world == 1 or dist.get_backend() == "nccl"):
+            ctx = self.net.ctx
+            if world == 1:
+                pred_map, pred_inst, table, offs, pts = ctx.infer_tile(img, win, self.batch_size)
+                return np.squeeze(pred_map), pred_inst, table_to_dict(table, offs, pts, self.nr_types)
+            import torch
+            H, W = img.shape[:2]
+            rows, cols = ctx.tile_grid(H, W, win)
+            lo, hi = shard_range(rows * cols, dist.get_rank(), world)
+            d_img = torch.from_numpy(np.ascontiguousarray(img)).cuda()
+            d_pred = torch.zeros((H, W, ctx.out_shape(win, win)[2]), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()  # torch's stream -> the library's stream
+            ctx.tile_predict_dev(d_img.data_ptr(), H, W, win, lo, hi, self.batch_size, d_pred.data_ptr())
+            ctx.sync()
+            dist.all_reduce(d_pred)
+            pred_map = d_pred.cpu().numpy()
+        else:
+            src_shape = img.shape
+            padded, patch_info, _ = _prepare_patching(img, self.patch_input_shape, self.patch_output_shape, True)
+            outs = run_patches(padded, patch_info, self.patch_input_shape, self.run_step, self.batch_size)
+            pred_map = _stitch(patch_info, outs, src_shape)
         pred_inst, inst_info_dict = self.post_proc_func(pred_map, nr_types=self.nr_types, return_centroids=True)
         return np.squeeze(pred_map), pred_inst, inst_info_dict
 

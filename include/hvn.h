@@ -113,6 +113,24 @@ int hvn_forward_postproc(hvn_ctx *ctx, const uint8_t *imgs_host, int B, int H, i
 int hvn_forward_postproc_dev(hvn_ctx *ctx, const uint8_t *imgs_dev, int B, int H, int W, float *pred_dev,
                              int32_t *inst_dev, int64_t *table_dev, int max_rows, int32_t *n_rows_dev);
 
+/* ---- whole-image tile path (reference infer/tile.py:46-143: `_prepare_patching`, the batch loop, the stitch +
+ * crop of `_post_process_patches`, then `process`): img u8 [H,W,3] RGB; patch_in = 256 (fast) / 270 (original).
+ * Reflect padding, patch extraction, stitching and cropping are index arithmetic on the device; the padded image,
+ * the patch list and the stitched map never exist on the host.
+ *   hvn_tile_grid        : rows x cols of the patch grid (tile.py:60-69).
+ *   hvn_tile_predict_dev : grid cells [cell_lo, cell_hi) (row-major) -> their region of pred_dev [H,W,C]; other
+ *                          pixels are untouched (multi-GPU: each rank runs its slice into a zeroed map, then the maps
+ *                          are summed -- x + 0 is exact).  batch = patches per network call (0 = default).
+ *   hvn_infer_tile       : everything for one image from host buffers: pred_host [H,W,C] (may be NULL), inst [H,W],
+ *                          table [max_rows,10], n_rows [1], and -- when offs_host is not NULL -- contours as in
+ *                          hvn_contours (offs [max_rows + 1], pts [pts_cap,2]). */
+int hvn_tile_grid(const hvn_ctx *ctx, int H, int W, int patch_in, int *rows, int *cols);
+int hvn_tile_predict_dev(hvn_ctx *ctx, const uint8_t *img_dev, int H, int W, int patch_in, int cell_lo, int cell_hi,
+                         int batch, float *pred_dev);
+int hvn_infer_tile(hvn_ctx *ctx, const uint8_t *img_host, int H, int W, int patch_in, int batch, float *pred_host,
+                   int32_t *inst_host, int64_t *table_host, int max_rows, int32_t *n_rows_host, int32_t *pts_host,
+                   int64_t pts_cap, int32_t *offs_host);
+
 /* ---- device memory / stream helpers for callers without a CUDA binding of their own. */
 int hvn_malloc(hvn_ctx *ctx, size_t bytes, void **dev_ptr);
 int hvn_free(hvn_ctx *ctx, void *dev_ptr);
