@@ -87,10 +87,12 @@ def peaks():
 def measured_traffic(kernel_class):
     """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture (profiles/)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        import glob
+        path = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))[-1]  # latest committed capture
+        t = json.load(open(path))
         k = t["kernels"].get("k_conv_tc" if kernel_class == "conv_tc" else "k_conv_ref")
         return {"dram_bytes_per_launch": k["dram_bytes"] / k["launches"], "launches": k["launches"], "batch": t["batch"],
-                "source": "profiles/r1_traffic.json (" + t["command"] + ")"}
+                "source": "profiles/" + os.path.basename(path) + " (" + t["command"] + ")"}
     except Exception:
         return None
 

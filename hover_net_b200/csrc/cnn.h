@@ -63,7 +63,7 @@ class Model {
     std::map<std::string, int> index;
     std::map<std::string, std::vector<float>> host;
     bool finalized = false;
-    int tc_halo = 0;         // k x k stride-1 layers from one halo tile per channel block: 0 off (measured slower), 1 thin layers, 2 all eligible
+    int tc_halo = 1;         // k x k stride-1 layers from one halo tile per channel block: 0 off, 1 where its 8 x 16 tiling fits, 2 all eligible
     int fuse_up2 = 0;        // 1: 2x upsample + skip add inside the conv epilogue; 0: separate streaming pass (faster)
     int fuse_shortcut = 1;   // fold each residual group's 1x1 shortcut into unit 0's conv3 (one GEMM over [a2 | x])
     int xform = 1;           // fuse pre-activation BN+ReLU into the consuming 1x1 conv's A-operand load

@@ -109,9 +109,11 @@ __device__ __forceinline__ void store_split4(const SplitRef &o, long long off, c
     *reinterpret_cast<uint2 *>(o.lo + off) = ol;
 }
 
+// sc / sh: the BN scale / shift of channels c..c+3, loaded once per tile by the caller (they do not depend
+// on the pixel; loading them per store left the write-out loop waiting on global loads).
 template <int MODE>
 __device__ __forceinline__ void epi_finish(const ConvParams &P, int n, int oy, int ox, int c, float v[4],
-                                           const EpiPre<MODE> &pre) {
+                                           const EpiPre<MODE> &pre, const float4 &s, const float4 &b) {
     if constexpr (MODE == EPI_RES) { v[0] += pre.r.x; v[1] += pre.r.y; v[2] += pre.r.z; v[3] += pre.r.w; }
     if (P.out_raw.p) {
         float *o = P.out_raw.p + n * P.out_raw.sN + (long long)oy * P.out_raw.sH + (long long)ox * P.out_raw.sW + c;
@@ -130,11 +132,7 @@ __device__ __forceinline__ void epi_finish(const ConvParams &P, int n, int oy, i
         }
     } else if (P.out_split.hi) {
         float t[4] = {v[0], v[1], v[2], v[3]};
-        if (P.scale) {
-            const float4 s = *reinterpret_cast<const float4 *>(P.scale + c);
-            const float4 b = *reinterpret_cast<const float4 *>(P.shift + c);
-            t[0] = t[0] * s.x + b.x; t[1] = t[1] * s.y + b.y; t[2] = t[2] * s.z + b.z; t[3] = t[3] * s.w + b.w;
-        }
+        if (P.scale) { t[0] = t[0] * s.x + b.x; t[1] = t[1] * s.y + b.y; t[2] = t[2] * s.z + b.z; t[3] = t[3] * s.w + b.w; }
         if (P.relu) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) t[i] = fmaxf(t[i], 0.f);

@@ -142,70 +142,91 @@ void launch_conv_ref(const ConvParams &P, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // stem: x/255 -> 7x7 conv (3->64, fp32) -> BN+ReLU -> split.  pad = 3 in `fast` mode, 0 otherwise.
+// One block = 128 consecutive output pixels of one row; a thread owns 4 pixels x 16 output channels
+// (64 accumulators), so every input value and every weight float4 read from shared memory feeds 16 FMAs
+// (8 shared loads per 64 FMAs; the per-pixel form it replaces issued 16 loads per 64).  The 7 input rows
+// of the segment are staged as floats already divided by 255 (the reference's own `imgs / 255.0`), zero
+// outside the image.  Accumulation order per output is (ky, kx, channel), as in the reference's direct sum.
+constexpr int C0_PX = 128, C0_IN = (C0_PX + 6) * 3;
 __global__ void __launch_bounds__(128) k_conv0(const uint8_t *__restrict__ img, int B, int H, int W, int pad,
                                                const float *__restrict__ wgt /*[7][7][3][64]*/,
                                                const float *__restrict__ scale, const float *__restrict__ shift,
                                                SplitRef out) {
-    extern __shared__ float s_w[];  // 7*7*3*64 floats
-    for (int i = threadIdx.x; i < 7 * 7 * 3 * 64; i += blockDim.x) s_w[i] = wgt[i];
-    __syncthreads();
-    const int ho = out.h, wo = out.w;
-    long long M = (long long)B * ho * wo;
-    long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    int n = (int)(m / ((long long)ho * wo));
-    int r = (int)(m - (long long)n * ho * wo);
-    int oy = r / wo, ox = r - oy * wo;
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    extern __shared__ float s_w[];          // 7*7*3*64 weights, then 7 x C0_IN input floats
+    float *s_in = s_w + 7 * 7 * 3 * 64;
+    const int t = threadIdx.x, ho = out.h, wo = out.w;
+    const int x0 = blockIdx.x * C0_PX, oy = blockIdx.y, n = blockIdx.z;
+    (void)B; (void)ho;
+    for (int i = t; i < 7 * 7 * 3 * 64 / 4; i += 128)
+        reinterpret_cast<float4 *>(s_w)[i] = reinterpret_cast<const float4 *>(wgt)[i];
     const uint8_t *im = img + (size_t)n * H * W * 3;
+    for (int i = t; i < 7 * C0_IN; i += 128) {
+        const int row = i / C0_IN, col = i - row * C0_IN;
+        const int pxi = col / 3, ch = col - pxi * 3;
+        const int iy = oy + row - pad, ix = x0 + pxi - pad;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = (float)im[((size_t)iy * W + ix) * 3 + ch] / 255.0f;
+        s_in[i] = v;
+    }
+    __syncthreads();
+    const int cg = t & 3, pq = t >> 2;      // 16-channel group, pixel quad
+    float acc[4][16];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[p][j] = 0.f;
     for (int ky = 0; ky < 7; ++ky) {
-        int iy = oy + ky - pad;
-        if (iy < 0 || iy >= H) continue;
+        const float *in_row = s_in + ky * C0_IN + pq * 12;
+#pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-            int ix = ox + kx - pad;
-            if (ix < 0 || ix >= W) continue;
-            const uint8_t *px = im + ((size_t)iy * W + ix) * 3;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float v = (float)px[ch] / 255.0f;
-                const float4 *wr = reinterpret_cast<const float4 *>(s_w + ((ky * 7 + kx) * 3 + ch) * 64);
+                float v[4];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float4 w4 = wr[j];
-                    acc[4 * j + 0] = fmaf(v, w4.x, acc[4 * j + 0]);
-                    acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
-                    acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
-                    acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+                for (int p = 0; p < 4; ++p) v[p] = in_row[(p + kx) * 3 + ch];
+                const float4 *wr = reinterpret_cast<const float4 *>(s_w + ((ky * 7 + kx) * 3 + ch) * 64 + cg * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w4 = wr[j];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        acc[p][4 * j + 0] = fmaf(v[p], w4.x, acc[p][4 * j + 0]);
+                        acc[p][4 * j + 1] = fmaf(v[p], w4.y, acc[p][4 * j + 1]);
+                        acc[p][4 * j + 2] = fmaf(v[p], w4.z, acc[p][4 * j + 2]);
+                        acc[p][4 * j + 3] = fmaf(v[p], w4.w, acc[p][4 * j + 3]);
+                    }
                 }
             }
         }
     }
-    long long oo = n * out.sN + (long long)oy * out.sH + (long long)ox * out.sW;
+    float sc[16], sh[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        __half oh[4], ol[4];
+    for (int j = 0; j < 16; ++j) { sc[j] = scale[cg * 16 + j]; sh[j] = shift[cg * 16 + j]; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float t = fmaxf(acc[4 * j + i] * scale[4 * j + i] + shift[4 * j + i], 0.f);
-            split_f32(t, oh[i], ol[i]);
+    for (int p = 0; p < 4; ++p) {
+        const int ox = x0 + pq * 4 + p;
+        if (ox >= wo) continue;
+        const long long oo = n * out.sN + (long long)oy * out.sH + (long long)ox * out.sW + cg * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float tv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tv[i] = fmaxf(acc[p][4 * j + i] * sc[4 * j + i] + sh[4 * j + i], 0.f);
+            store_split4(out, oo + 4 * j, tv);
         }
-        *reinterpret_cast<uint2 *>(out.hi + oo + 4 * j) = *reinterpret_cast<uint2 *>(oh);
-        *reinterpret_cast<uint2 *>(out.lo + oo + 4 * j) = *reinterpret_cast<uint2 *>(ol);
     }
 }
 
 void launch_conv0(const uint8_t *img, int B, int H, int W, int pad, const float *wgt, const float *scale,
                   const float *shift, const SplitRef &out, cudaStream_t s) {
     static bool attr_set = false;
-    const int smem = 7 * 7 * 3 * 64 * 4;
+    const int smem = (7 * 7 * 3 * 64 + 7 * C0_IN) * 4;
     if (!attr_set) {
         cudaFuncSetAttribute(k_conv0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_set = true;
     }
-    long long M = (long long)B * out.h * out.w;
-    k_conv0<<<cdiv(M, 128), 128, smem, s>>>(img, B, H, W, pad, wgt, scale, shift, out);
+    dim3 grid(cdiv(out.w, C0_PX), out.h, B);
+    k_conv0<<<grid, 128, smem, s>>>(img, B, H, W, pad, wgt, scale, shift, out);
 }
 
 // ------------------------------------------------------------------------------------------------

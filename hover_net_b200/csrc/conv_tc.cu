@@ -307,10 +307,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
             // half: 2 instructions per K-step instead of 3; the epilogue sums the halves in fp32 registers.
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
           if constexpr (HALO) {
-            // it = kc * taps + tap (channel-slice major): all taps of a slice read the same halo slot
+            // it = kc * taps + tap (channel-slice major): all taps of a slice read the same halo slot.
+            // This one thread paces the tensor core, so its per-tap instruction count matters (measured: with two
+            // integer divisions and three descriptor builds per tap it issued 8 MMAs per ~1100 cycles, half the
+            // tensor core's rate): every index is carried incrementally and a descriptor is its constant upper
+            // part plus (address >> 4).
             const uint32_t sbo = (uint32_t)G.halo_w * 128u;
-            int ablk = 0, wit = 0, scount = 0, slot = 0;
+            const uint64_t adesc0 = umma_desc(0, sbo), bdesc0 = umma_desc(0);
+            const uint32_t a_lo_off = (uint32_t)G.a_plane >> 4;
+            int scount = 0;
+            uint32_t ws = 0, wph = 0;       // weight ring stage / phase
+            uint32_t slot = 0, aph_h = 0;   // halo slot / phase
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int tap = 0, ky = 0, kx = 0;
                 for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
                     const int as = scount & 1;
                     const uint32_t aph = (uint32_t)(scount >> 1) & 1u;
@@ -318,28 +327,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BLOCK_N);
                     const int it1 = min(it0 + G.seg, kiters);
-                    for (int it = it0; it < it1; ++it, ++wit) {
-                        const int kc = it / taps, tap = it - kc * taps;
-                        if (tap == 0) {
-                            slot = ablk % G.na;
-                            mbar_wait(rfull_bar(slot), (uint32_t)(ablk / G.na) & 1u);
-                        }
-                        const int s = wit % STAGES;
-                        mbar_wait(full_bar(s), (uint32_t)(wit / STAGES) & 1u);
+                    for (int it = it0; it < it1; ++it) {
+                        if (tap == 0) mbar_wait(rfull_bar(slot), aph_h);
+                        mbar_wait(full_bar(ws), wph);
                         tc_fence_after();
-                        const int ky = tap / P.w.kw, kx = tap - ky * P.w.kw;
-                        const uint32_t a0 = raw_base + (uint32_t)(slot * 2 * G.a_plane) + (uint32_t)((ky * G.halo_w + kx) * 128);
-                        const uint32_t sb = smem_base + s * STAGE_BYTES;
-                        const uint64_t da_hi = umma_desc(a0, sbo), da_lo = umma_desc(a0 + (uint32_t)G.a_plane, sbo),
-                                       db_hi = umma_desc(sb);  // [w_hi | w_lo]: 2*BLOCK_N contiguous rows
+                        const uint32_t a0 = raw_base + slot * (uint32_t)(2 * G.a_plane) + (uint32_t)((ky * G.halo_w + kx) * 128);
+                        const uint64_t da_hi = adesc0 + (uint64_t)((a0 & 0x3FFFFu) >> 4), da_lo = da_hi + a_lo_off,
+                                       db_hi = bdesc0 + (uint64_t)(((smem_base + ws * STAGE_BYTES) & 0x3FFFFu) >> 4);  // [w_hi | w_lo]
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t ko = (uint64_t)(2 * k);
                             tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc2, (it > it0 || k > 0) ? 1u : 0u);
                             tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
                         }
-                        tc_commit(empty_bar(s));
-                        if (tap == taps - 1) { tc_commit(rempty_bar(slot)); ++ablk; }  // halo slot reusable
+                        tc_commit(empty_bar(ws));
+                        if (++ws == (uint32_t)STAGES) { ws = 0; wph ^= 1u; }
+                        if (++kx == P.w.kw) { kx = 0; ++ky; }
+                        if (++tap == taps) {  // last tap of this channel slice: the halo slot is reusable
+                            tc_commit(rempty_bar(slot));
+                            tap = 0; ky = 0; kx = 0;
+                            if (++slot == (uint32_t)G.na) { slot = 0; aph_h ^= 1u; }
+                        }
                     }
                     tc_commit(tfull_bar(as));
                 }
@@ -478,6 +486,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     }
                 }
             }
+            // BN scale / shift of this lane's 4 channels per 32-channel block: requested before the accumulator wait
+            float4 esc[NCH], esh[NCH];
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {
+                esc[cc] = make_float4(1.f, 1.f, 1.f, 1.f); esh[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE != EPI_UP2 && P.scale && P.out_split.hi) {
+                    esc[cc] = *reinterpret_cast<const float4 *>(P.scale + tn * BLOCK_N + cb + cc * 32 + sub_g * 4);
+                    esh[cc] = *reinterpret_cast<const float4 *>(P.shift + tn * BLOCK_N + cb + cc * 32 + sub_g * 4);
+                }
+            }
             float acc[CW];
 #pragma unroll
             for (int j = 0; j < CW; ++j) acc[j] = 0.f;
@@ -543,7 +561,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         const float4 t = *reinterpret_cast<const float4 *>(&ep_tile[src * 32 + ((sub_g ^ (src & 7)) << 2)]);
                         if (pv[u]) {
                             float v[4] = {t.x, t.y, t.z, t.w};
-                            epi_finish<MODE>(P, pn[u], py[u], px[u], ch, v, pre[u]);
+                            epi_finish<MODE>(P, pn[u], py[u], px[u], ch, v, pre[u], esc[c0 / 32], esh[c0 / 32]);
                         }
                     }
                 }
@@ -600,7 +618,7 @@ static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *d
 static int g_force_block_n = 0;
 static int g_seg_chunks = 4;  // 64-channel slices per accumulation segment (4 -> 48 chained MMAs)
 static int g_res_tma = 1, g_res_tma_max_chunks = 4;  // residual tile via TMA for 1x1 layers with K <= 256 (larger K: A re-reads of N=64 tiles cost more)
-static int g_halo = 1;  // 0 off, 1 auto (thin k x k layers: cout tile <= 64, or >= 25 taps), 2 every eligible layer
+static int g_halo = 1;  // 0 off, 1 auto (where the fixed 8 x 16 tiling fits the output map), 2 every eligible layer
 void tc_set_halo(int mode) { g_halo = mode; }
 void tc_set_res_tma(int on) { g_res_tma = on; }
 void tc_set_block_n(int n) { g_force_block_n = n; }
@@ -653,8 +671,19 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
         }
     }
     plan.halo = 0;
-    if (g_halo && w.taps > 1 && P.stride == 1 && !xf && !two && !P.up2 && !P.res.p && w.kh <= 5 && w.kw <= 5 &&
-        (g_halo >= 2 || bn <= 64 || w.taps >= 25)) {
+    bool want_halo = g_halo && w.taps > 1 && P.stride == 1 && !xf && !two && !P.up2 && !P.res.p && w.kh <= 5 && w.kw <= 5;
+    if (want_halo && g_halo == 1) {
+        // auto: the halo variant tiles the output in fixed 8 x 16 rectangles; take it only where that wastes at most
+        // ~7 % more accumulator rows than the best free-form rectangle of the per-tap path (measured per layer:
+        // 1.05-1.10x where the tilings match, a loss on the small odd-sized decoder maps)
+        double best = 0;
+        for (int bw = 1; bw <= 128; ++bw)
+            for (int bh = std::min(128 / bw, 256); bh >= 1; --bh)
+                best = std::max(best, (double)P.ho * P.wo / ((double)cdiv(P.wo, bw) * cdiv(P.ho, bh) * 128.0));
+        const double cov = (double)P.ho * P.wo / ((double)cdiv(P.wo, 8) * cdiv(P.ho, 16) * 128.0);
+        want_halo = cov >= 0.93 * best;
+    }
+    if (want_halo) {
         plan.halo = 1;
         plan.bw = 8; plan.bh = 16;   // one 8-pixel row per swizzle group, 16 rows = the 128 accumulator rows
         plan.halo_w = plan.bw + w.kw - 1; plan.halo_h = plan.bh + w.kh - 1;

@@ -227,3 +227,62 @@ def test_cli_builds_reference_run_args():
     with pytest.raises(Exception, match="model path"):
         run_infer.parse(["tile", "--input_dir=a", "--output_dir=b"])
     assert run_infer.parse(["--help"])[0] is None
+
+
+@pytest.mark.gpu
+def test_cli_wsi_end_to_end_on_device(tmp_path, oracle_pp):
+    """`run_infer.py ... wsi` on a synthetic `.npy` slide with the real network: sampled patches of the
+    slide-sized prediction map agree with the CPU oracle network (<= 1e-4), and the JSON equals the
+    three-phase merge re-run with the oracle's `process` on the same prediction map (bit-exact)."""
+    import torch
+    from hover_net_b200 import run_infer, synth
+    from oracle import hovernet_torch as O
+
+    mode, nt = "fast", 6
+    h, w = 600, 700
+    base = synth.make_patches(12, 256, seed=60)
+    img = np.concatenate([np.concatenate(list(base[r * 3:(r + 1) * 3]), 1) for r in range(3)], 0)[:h, :w].copy()
+    os.makedirs(tmp_path / "in")
+    np.save(str(tmp_path / "in" / "slide.npy"), img)
+    sd = synth.make_state_dict(mode, nt, seed=0)
+    np.savez(str(tmp_path / "ckpt.npz"), **sd)
+    import cv2
+    os.makedirs(tmp_path / "msk")
+    cv2.imwrite(str(tmp_path / "msk" / "slide.png"), np.full((h // 8, w // 8), 255, np.uint8))
+    argv = ["--nr_types=6", "--model_mode=fast", "--model_path=%s" % (tmp_path / "ckpt.npz"), "--batch_size=8", "wsi",
+            "--input_dir=%s" % (tmp_path / "in"), "--output_dir=%s" % (tmp_path / "out"), "--cache_path=%s" % (tmp_path / "cache"),
+            "--input_mask_dir=%s" % (tmp_path / "msk"), "--chunk_shape=500", "--tile_shape=256", "--ambiguous_size=32"]
+    cmd, margs, rargs, _ = run_infer.parse(argv)
+    assert cmd == "wsi"
+    margs["method"]["model_args"]["device"] = 0
+    mgr = wsi.InferManager(**margs)
+    mgr.process_wsi_list(rargs)
+    js = json.load(open(str(tmp_path / "out" / "slide.json")))
+    assert js["mag"] == 40 and len(js["nuc"]) > 0
+    pred = np.array(mgr.wsi_pred_map)
+    assert pred.shape == (h, w, 4)
+    # (1) network: three patches of the grid against the CPU oracle network
+    _, pinfo = wsi._get_chunk_patch_info(np.array([h, w]), np.array([500, 500]), np.array([256, 256]), np.array([164, 164]))
+    assert pinfo.shape[0] == 16
+    tsd = O.to_torch_state_dict(sd)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    for k in (0, 5, 15):
+        y, x = (int(v) for v in pinfo[k, 0, 0])
+        ref = O.infer_step(img[None, y:y + 256, x:x + 256], tsd, mode, nt)[0]
+        got = pred[y + 46:y + 46 + 164, x + 46:x + 46 + 164]
+        assert np.abs(got[..., 1:] - ref[..., 1:]).max() <= 1e-4
+        assert (got[..., 0] != ref[..., 0]).mean() < 2e-3
+    assert np.all(pred[:46] == 0) and np.all(pred[:, :46] == 0)  # the border the patch grid never covers stays empty
+    # (2) merge: same phases with the oracle's process on the same map
+    ref_mgr = wsi.InferManager.__new__(wsi.InferManager)
+    ref_mgr.__dict__.update({k: v for k, v in mgr.__dict__.items() if k not in ("net", "run_step", "wsi_inst_info", "wsi_inst_map")})
+    ref_mgr.post_proc_func = oracle_pp.process
+    ref_mgr._get_raw_prediction = lambda ci, pi: ref_mgr.wsi_pred_map.__setitem__(slice(None), pred)
+    ref_mgr.process_single_file(str(tmp_path / "in" / "slide.npy"), str(tmp_path / "msk" / "slide.png"), str(tmp_path / "ref"))
+    assert sorted(ref_mgr.wsi_inst_info.keys()) == sorted(mgr.wsi_inst_info.keys()) == sorted(int(k) for k in js["nuc"])
+    assert np.array_equal(ref_mgr.wsi_inst_map, mgr.wsi_inst_map)
+    for k, v in ref_mgr.wsi_inst_info.items():
+        j = js["nuc"][str(k)]
+        assert j["bbox"] == v["bbox"].tolist() and j["centroid"] == v["centroid"].tolist()
+        assert j["contour"] == v["contour"].tolist() and j["type"] == v["type"] and j["type_prob"] == v["type_prob"]
+    mgr.net.ctx.close()

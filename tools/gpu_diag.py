@@ -53,6 +53,8 @@ def _knobs(net):
     """development knobs from the environment: HVN_TC_HALO=0|1|2"""
     if os.environ.get("HVN_TC_HALO"):
         net.ctx.set_option("tc_halo", int(os.environ["HVN_TC_HALO"]))
+    if os.environ.get("HVN_TC_SEG"):
+        net.ctx.set_option("tc_seg_chunks", int(os.environ["HVN_TC_SEG"]))
 
 
 def tc(mode="fast", nt=6, verbose=False):

@@ -9,6 +9,8 @@ from hover_net_b200.models.hovernet.net_desc import create_model
 net = create_model(mode="fast", nr_types=6)
 net.load_state_dict(synth.make_state_dict("fast", 6, 0))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+if os.environ.get("HVN_TC_HALO"):  # development knob: 0 | 1 | 2
+    net.ctx.set_option("tc_halo", int(os.environ["HVN_TC_HALO"]))
 net.ctx.set_option("chunk", B)
 net.ctx.set_option("branch_streams", 0)
 x = np.concatenate([synth.make_patches(8, 256, seed=1)] * ((B + 7) // 8))[:B]
