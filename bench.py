@@ -343,8 +343,9 @@ def run_ours(args):
                          "algorithmic_gflop_per_launch": d["gflop"] / max(1, d["launches"]),
                          "avg_launch_ms": d["ms"] / max(1, d["launches"]), "launches_per_step": d["launches"],
                          "traffic": measured_traffic(dom),
-                         "note": "algorithmic 2*MACs of the reference graph; the kernel issues 3 fp16 MMAs per "
-                                 "product (hi*hi+hi*lo+lo*hi), so frac <= 1/3 by construction"},
+                         "note": "algorithmic 2*MACs of the reference graph; every product is formed three times in "
+                                 "fp16 (hi*hi+hi*lo+lo*hi, issued as two MMA instructions per K-step), so frac <= 1/3 "
+                                 "by construction"},
             "kernel_classes": prof,
             "algorithmic_gflop_per_tile": flops_step / B / 1e9,
             "postproc_ms_per_tile": prof["postproc"]["ms"] / B,

@@ -165,3 +165,51 @@ def test_config3_4k_tile_single_gpu_properties():
     _, pred_inst2, _ = mgr.infer_image(img)
     assert np.array_equal(pred_inst, pred_inst2)
     mgr.net.ctx.close()
+
+
+def _two_rank_tile_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from hover_net_b200 import synth
+    from hover_net_b200.infer.tile import InferManager
+    mode, nt = "fast", 6
+    base = synth.make_patches(6, 256, seed=70)
+    img = np.concatenate([np.concatenate(list(base[r * 3:(r + 1) * 3]), 1) for r in range(2)], 0)[:500, :610].copy()
+    mgr = InferManager(method={"model_args": {"nr_types": nt, "mode": mode, "device": rank},
+                               "model_path": synth.make_state_dict(mode, nt, seed=0)}, type_info_path=None)
+    mgr.patch_input_shape, mgr.patch_output_shape, mgr.batch_size = 256, 164, 4
+    pred, inst, info = mgr.infer_image(img)                       # patch grid sharded over the ranks + all_reduce
+    one = mgr.net.ctx.infer_tile(img, 256, 4)                     # the same image on this rank alone
+    ok = bool(np.array_equal(pred, one[0]) and np.array_equal(inst, one[1]) and len(info) > 0)
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        out.put((flags, int(inst.max()), len(info)))
+    dist.barrier()
+    mgr.net.ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_config3_tile_sharded_over_two_gpus_equals_single_gpu():
+    """configs[3] plumbing on real devices: one image, patch grid split over 2 ranks, maps summed by one NCCL
+    all_reduce (disjoint supports) == the single-GPU device path, bit for bit, on both ranks."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_rank_tile_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flags, max_id, n_info = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert flags == [True, True] and max_id > 0 and n_info > 0

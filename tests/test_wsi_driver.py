@@ -266,7 +266,7 @@ def test_cli_wsi_end_to_end_on_device(tmp_path, oracle_pp):
     assert pinfo.shape[0] == 16
     tsd = O.to_torch_state_dict(sd)
     torch.set_num_threads(min(32, os.cpu_count() or 1))
-    for k in (0, 5, 15):
+    for k in (0, 5, 10):  # (the last grid row / column sticks out of the slide and belongs to no chunk, as in the reference)
         y, x = (int(v) for v in pinfo[k, 0, 0])
         ref = O.infer_step(img[None, y:y + 256, x:x + 256], tsd, mode, nt)[0]
         got = pred[y + 46:y + 46 + 164, x + 46:x + 46 + 164]
@@ -278,6 +278,7 @@ def test_cli_wsi_end_to_end_on_device(tmp_path, oracle_pp):
     ref_mgr.__dict__.update({k: v for k, v in mgr.__dict__.items() if k not in ("net", "run_step", "wsi_inst_info", "wsi_inst_map")})
     ref_mgr.post_proc_func = oracle_pp.process
     ref_mgr._get_raw_prediction = lambda ci, pi: ref_mgr.wsi_pred_map.__setitem__(slice(None), pred)
+    os.makedirs(tmp_path / "ref")
     ref_mgr.process_single_file(str(tmp_path / "in" / "slide.npy"), str(tmp_path / "msk" / "slide.png"), str(tmp_path / "ref"))
     assert sorted(ref_mgr.wsi_inst_info.keys()) == sorted(mgr.wsi_inst_info.keys()) == sorted(int(k) for k in js["nuc"])
     assert np.array_equal(ref_mgr.wsi_inst_map, mgr.wsi_inst_map)
