@@ -187,10 +187,16 @@ class InferManager(base.InferManager):
         file_path_list = glob.glob(patterning("%s/*" % self.input_dir))
         file_path_list.sort()  # ensure same order
         assert len(file_path_list) > 0, "Not Detected Any Files From Path"
-        for sub in ("json", "mat", "overlay"):
-            _rm_n_mkdir(self.output_dir + "/%s/" % sub)
-        if self.save_qupath:
-            _rm_n_mkdir(self.output_dir + "/qupath/")
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        rank = dist.get_rank() if multi else 0
+        if rank == 0:  # every rank computes (the patch grid of each image is sharded); rank 0 alone writes
+            for sub in ("json", "mat", "overlay"):
+                _rm_n_mkdir(self.output_dir + "/%s/" % sub)
+            if self.save_qupath:
+                _rm_n_mkdir(self.output_dir + "/qupath/")
+        if multi:
+            dist.barrier()
 
         for file_path in file_path_list:
             img = cv2.imread(file_path)
@@ -199,6 +205,8 @@ class InferManager(base.InferManager):
             img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
             img_name = pathlib.Path(file_path).stem
             pred_map, pred_inst, inst_info_dict = self.infer_image(img)
+            if rank != 0:
+                continue
 
             nuc_val_list = list(inst_info_dict.values())
             nuc_uid_list = np.array(list(inst_info_dict.keys()))[:, None]  # singleton to make matlab happy

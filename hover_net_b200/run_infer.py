@@ -112,6 +112,7 @@ def main(argv=None):
             print(VERSION)
         else:
             print(__doc__)
+            _top_parser().print_help()
             _tile_parser().print_help()
             _wsi_parser().print_help()
         return 0

@@ -287,3 +287,52 @@ def test_cli_wsi_end_to_end_on_device(tmp_path, oracle_pp):
         assert j["bbox"] == v["bbox"].tolist() and j["centroid"] == v["centroid"].tolist()
         assert j["contour"] == v["contour"].tolist() and j["type"] == v["type"] and j["type_prob"] == v["type_prob"]
     mgr.net.ctx.close()
+
+
+def _raw_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(os.path.join(GOLD, "wsi_raw_fast.npz"))
+    h, w, chunk, pin, pout, seed = (int(v) for v in g["args"])
+    img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    mgr = _manager(h, w, 256, 32, chunk, pin, pout, 5, g["mask"])
+    mgr.wsi_handler = _ArrayHandler(img)
+    mgr.run_step = _fake_run_step
+    mgr.batch_size = 3
+    mgr.wsi_pred_map = np.zeros((h, w, 4), np.float32)
+    ci, pi = wsi._get_chunk_patch_info(np.array([h, w]), np.array([chunk, chunk]), np.array([pin, pin]), np.array([pout, pout]))
+    mgr._get_raw_prediction(ci, pi)
+    ok = bool(np.array_equal(mgr.wsi_pred_map, g["pred"].astype(np.float32)))
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        out.put(flags)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_raw_prediction_sharded_gloo_world2_equals_reference():
+    """configs[4] plumbing: the patches of every chunk sharded over 2 ranks and exchanged with one all_gather
+    per chunk -> every rank holds the reference's slide-sized prediction map."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_raw_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flags = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert flags == [True, True]
+
+
+def test_cli_help_and_version(capsys):
+    from hover_net_b200 import run_infer
+    assert run_infer.main(["--version"]) == 0
+    assert run_infer.VERSION in capsys.readouterr().out
+    assert run_infer.main(["--help"]) == 0
+    out = capsys.readouterr().out
+    assert "--model_path" in out and "--tile_shape" in out and "--save_qupath" in out
