@@ -152,7 +152,7 @@ class Context:
             max_rows = max(16, H * W // 64)
         if pts_cap is None:
             pts_cap = max(4096, n * H * W // 16)
-        while True:
+        for _attempt in range(4):  # at most: grow the table once, then the point buffer once
             inst = np.empty((n, H, W), dtype=np.int32)
             table = np.zeros((n, max_rows, ROW_LEN), dtype=np.int64)
             nrows = np.zeros((n,), dtype=np.int32)
@@ -172,6 +172,7 @@ class Context:
                 continue
             check(rc)
             return inst, table, nrows, offs, pts[: int(offs[-1])]
+        raise HvnError(-4, "postproc_contours: capacity retries exhausted")
 
     def contours_dev(self, d_inst, d_table, d_nrows, n, H, W, max_rows, d_pts, pts_cap, d_offs):
         L = lib()
@@ -200,7 +201,7 @@ class Context:
         L.hvn_infer_tile.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
-        while True:
+        for _attempt in range(4):
             pred = np.empty((H, W, oc), dtype=np.float32) if want_pred else None
             inst = np.empty((H, W), dtype=np.int32)
             table = np.zeros((max_rows, ROW_LEN), dtype=np.int64)
@@ -218,6 +219,7 @@ class Context:
             check(rc)
             n = int(nrows[0])
             return pred, inst, table[:n], offs, (pts[: int(offs[-1])] if contours else None)
+        raise HvnError(-4, "infer_tile: capacity retries exhausted")
 
     def tile_predict_dev(self, d_img, H, W, patch_in, cell_lo, cell_hi, batch, d_pred):
         L = lib()

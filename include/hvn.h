@@ -67,7 +67,11 @@ int hvn_finalize_weights(hvn_ctx *ctx);
  *                      2 = auto + run every tcgen05 layer against the referee kernel and record the
  *                      per-layer max differences (hvn_debug_log);
  *                      "chunk" = patches per internal sub-batch (0 = auto);
- *                      "profile" = 0 | 1 | 2 (see hvn_stage_ms). */
+ *                      "profile" = 0 | 1 | 2 (see hvn_stage_ms);
+ *                      tuning knobs (defaults are the measured best): "tc_halo" = 0 | 1 | 2 (k x k layers read
+ *                      shifted windows of one halo tile: off / where its 8x16 tiling fits / every eligible layer),
+ *                      "tc_seg_chunks" (64-channel slices per accumulation segment), "tc_block_n", "tc_res_tma",
+ *                      "xform", "fuse_shortcut", "fuse_up2", "branch_streams", "flood_impl". */
 int hvn_set_option(hvn_ctx *ctx, const char *key, int64_t value);
 const char *hvn_debug_log(const hvn_ctx *ctx);
 /* counters: "kernel_launches", "tc_launches", "pp_launches" (post-processing and contour kernels), "last_flops" (algorithmic 2*MACs of the

@@ -301,7 +301,7 @@ typedef struct {
 API void hvo_proc_np_hv(const float *pred, int cs, int H, int W, int32_t *inst, hvo_stages_t *st)
 {
     int n = H * W;
-    int32_t *blb = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t *blb = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     int32_t *lab = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
     float *hraw = (float *)malloc(sizeof(float) * (size_t)n);
     float *vraw = (float *)malloc(sizeof(float) * (size_t)n);
