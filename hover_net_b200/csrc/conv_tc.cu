@@ -13,20 +13,20 @@
 //   the two weight tiles are adjacent in shared memory) and a_lo x w_hi (N = BLOCK_N); the epilogue sums the
 //   halves: hi*hi + hi*lo + lo*hi, fp32 accumulation => fp32-grade products from fp16 tensor cores.
 // * Persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM
-//   allocator), warps 2..5 = epilogue (tcgen05.ld -> registers -> fused BN/ReLU/residual/upsample ->
-//   global).  Shared-memory ring of STAGES operand slots; two TMEM accumulator buffers so the epilogue
+//   allocator), warps 2..9 = epilogue (tcgen05.ld -> registers -> fused BN/ReLU/residual/upsample ->
+//   global).  Shared-memory ring of STAGES operand slots; two TMEM accumulation buffers so the epilogue
 //   of tile i overlaps the main loop of tile i+1.
 // * Accumulation precision: the tensor core adds into the fp32 accumulator with truncation, a bias
 //   that grows with the number of MMAs chained into one accumulator (measured on B200: ~4e-5
-//   relative at K=9216).  The K loop is therefore cut into segments of SEG_CHUNKS 64-channel slices
-//   (96 MMAs); each segment accumulates in its own TMEM buffer and the epilogue warps drain it into
+//   relative at K=9216).  The K loop is therefore cut into segments of 4 64-channel slices (32 MMA
+//   instructions); each segment accumulates in its own TMEM buffer and the epilogue warps drain it into
 //   fp32 registers (round-to-nearest adds) while the next segment runs in the other buffer.
 // * XF variant (1x1 layers fed by a raw fp32 tensor through a pre-activation BatchNorm+ReLU): four
 //   extra "transform" warps build the A tiles themselves -- coalesced fp32 loads, y=relu(x*scale+shift),
 //   fp16 hi/lo split, 128B-swizzled st.shared, fence.proxy.async -- so the pre-activated copy of the
 //   tensor never exists in HBM (no separate BN/ReLU pass, no second output of the producing layer).
-// * HALO variant (k x k stride-1 layers): the old path re-fetches the A tile once per filter tap, which
-//   makes thin layers (cout 32/64) L2->SM bandwidth bound (~6300 B/clk chip-wide).  Here ONE halo tile
+// * HALO variant (k x k stride-1 layers): the per-tap path re-fetches the A tile once per filter tap, which
+//   puts thin layers (cout 32/64) at the chip-wide L2->SM cap (~6300 B/clk, ncu: 11.2 TB/s).  Here ONE halo tile
 //   ((16+kh-1) x (8+kw-1) pixels x 64 channels, hi and lo) is fetched per 64-channel block and every tap's
 //   MMA reads its shifted 16x8 window straight out of it: the A descriptor starts (ky*Wp + kx) rows into the
 //   halo and steps SBO = Wp*128 B between 8-pixel rows.  tcgen05.mma resolves the 128B swizzle from absolute
