@@ -61,6 +61,37 @@ def main():
                             padded_shape=np.array(padded.shape), padded_sum=np.int64(padded.astype(np.int64).sum()),
                             padded_rowsum=padded.astype(np.int64).sum((1, 2)), stitched=captured["map"].astype(np.float32))
         print(name, padded.shape, pinfo.shape, captured["map"].shape)
+    gen_writers()
+
+
+def gen_writers():
+    """writers_tile.npz: the reference's QuPath TSV writer (convert_format.py:19-50) and typed overlay
+    (misc/viz_utils.py:94-125; typed colours are deterministic, per-instance random colours are not) on a
+    seeded instance dict."""
+    import importlib
+    import tempfile
+    conv = importlib.import_module("convert_format")
+    viz = importlib.import_module("misc.viz_utils")
+    rng = np.random.default_rng(99)
+    img = rng.integers(0, 256, (120, 150, 3), dtype=np.uint8)
+    type_info = {0: ("nolabe", (0, 0, 0)), 1: ("neopla", (255, 0, 0)), 2: ("inflam", (0, 255, 0)), 3: ("connec", (0, 0, 255))}
+    info = {}
+    for k in range(1, 9):
+        cy, cx, r = int(rng.integers(15, 105)), int(rng.integers(15, 135)), int(rng.integers(4, 12))
+        ang = np.linspace(0, 2 * np.pi, 12, endpoint=False)
+        cnt = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], -1).round().astype(np.int32)
+        info[k] = {"bbox": np.array([[cy - r, cx - r], [cy + r + 1, cx + r + 1]]), "centroid": np.array([cx + 0.25, cy + 0.5]),
+                   "contour": cnt, "type_prob": 0.5 + 0.05 * k, "type": int(k % 4)}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "a.tsv")
+        conv.to_qupath(path, [v["centroid"] for v in info.values()], [v["type"] for v in info.values()], type_info)
+        tsv = open(path).read()
+    over = viz.visualize_instances_dict(img, info, draw_dot=True, type_colour=type_info, line_thickness=2)
+    np.savez_compressed(os.path.join(OUT, "writers_tile.npz"), tsv=np.array(tsv), overlay=over.astype(np.uint8),
+                        ids=np.array(sorted(info.keys())), contour=np.stack([info[k]["contour"] for k in sorted(info)]),
+                        centroid=np.stack([info[k]["centroid"] for k in sorted(info)]),
+                        type=np.array([info[k]["type"] for k in sorted(info)]))
+    print("writers", over.shape, len(tsv), "bytes of tsv")
 
 
 if __name__ == "__main__":

@@ -213,3 +213,17 @@ def test_config3_tile_sharded_over_two_gpus_equals_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert flags == [True, True] and max_id > 0 and n_info > 0
+
+
+def test_writers_match_reference(tmp_path):
+    """QuPath TSV and the typed overlay vs the reference's own writers (goldens: oracle/gen_golden_tile.py)."""
+    g = np.load(os.path.join(GOLD, "writers_tile.npz"))
+    img = np.random.default_rng(99).integers(0, 256, (120, 150, 3), dtype=np.uint8)
+    type_info = {0: ("nolabe", (0, 0, 0)), 1: ("neopla", (255, 0, 0)), 2: ("inflam", (0, 255, 0)), 3: ("connec", (0, 0, 255))}
+    info = {int(k): {"contour": g["contour"][i], "centroid": g["centroid"][i], "type": int(g["type"][i])}
+            for i, k in enumerate(g["ids"])}
+    p = str(tmp_path / "a.tsv")
+    tile._to_qupath(p, [v["centroid"] for v in info.values()], [v["type"] for v in info.values()], type_info)
+    assert open(p).read() == str(g["tsv"])
+    over = tile._overlay(img, info, draw_dot=True, type_colour=type_info, line_thickness=2)
+    assert np.array_equal(over, g["overlay"])
