@@ -1,5 +1,6 @@
-"""Small end-to-end run for compute-sanitizer (memcheck): 1 fast-mode patch through CNN + post-processing,
-the CUDA-core referee path, and a 300x200 synthetic map through the generic (large-map) flood."""
+"""Small end-to-end run for compute-sanitizer (memcheck): 1 fast-mode patch through CNN + post-processing
+(tcgen05 path incl. the HALO variant and the stem), device contours, the whole-image tile path on a small image,
+and a 300x200 synthetic map through the generic (large-map) flood.  HVN_SAN_REFEREE=1 adds the CUDA-core referee."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,12 +9,20 @@ from hover_net_b200.models.hovernet.net_desc import create_model
 
 net = create_model(mode="fast", nr_types=6)
 net.load_state_dict(synth.make_state_dict("fast", 6, 0))
+net.ctx.set_option("tc_halo", 2)
 x = synth.make_patches(1, 256, seed=1)
 pred, inst, tab, n = net.ctx.forward_postproc(x)
 print("tc path ok", int(n[0]))
-net.ctx.set_option("conv_path", 1)
-pred2 = net.ctx.forward(x)
-print("referee path ok", float(np.abs(pred2[..., 1:] - pred[..., 1:]).max()))
+pm = synth.synth_pred_map(164, 164, 6, 0)
+gi, gt, gn, offs, pts = net.ctx.postproc_contours(pm, 6)
+print("contours ok", int(gn[0]), len(pts))
+img = np.concatenate([x[0], x[0][:, ::-1]], 1)[:200, :300]
+tp, ti, tt, toffs, tpts = net.ctx.infer_tile(img, 256, 4)
+print("tile path ok", len(tt), len(tpts))
+if os.environ.get("HVN_SAN_REFEREE"):
+    net.ctx.set_option("conv_path", 1)
+    pred2 = net.ctx.forward(x)
+    print("referee path ok", float(np.abs(pred2[..., 1:] - pred[..., 1:]).max()))
 pm = synth.synth_pred_map(300, 200, 6, 0)
 net.ctx.set_option("flood_impl", 2)
 gi, gt, gn = net.ctx.postproc(pm, 6)
