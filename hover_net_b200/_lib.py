@@ -293,6 +293,22 @@ class Context:
         check(lib().hvn_postproc_dev(self._h, _ptr(d_pred), n, H, W, C, int(nr_types or 0), _ptr(d_inst),
                                      _ptr(d_table), int(max_rows), _ptr(d_nrows)))
 
+    def pack_tables_dev(self, d_table, d_nrows, n, max_rows, d_packed, cap_rows, d_offs):
+        """padded tables [n,max_rows,10] -> packed rows [<=cap_rows,10] + offs [n+1] (all device pointers)."""
+        L = lib()
+        L.hvn_pack_tables_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        check(L.hvn_pack_tables_dev(self._h, _ptr(d_table), _ptr(d_nrows), int(n), int(max_rows), _ptr(d_packed),
+                                    int(cap_rows), _ptr(d_offs)))
+
+    def stream_handle(self):
+        """The context's cudaStream_t as an integer (e.g. for torch.cuda.ExternalStream)."""
+        p = ctypes.c_void_p()
+        L = lib()
+        L.hvn_get_stream.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+        check(L.hvn_get_stream(self._h, ctypes.byref(p)))
+        return int(p.value or 0)
+
     def forward_postproc_dev(self, d_imgs, B, H, W, d_pred, d_inst, d_table, max_rows, d_nrows):
         check(lib().hvn_forward_postproc_dev(self._h, _ptr(d_imgs), B, H, W, _ptr(d_pred), _ptr(d_inst),
                                              _ptr(d_table), int(max_rows), _ptr(d_nrows)))

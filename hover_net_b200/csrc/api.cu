@@ -475,6 +475,20 @@ int hvn_memcpy_d2h(hvn_ctx *c, void *dst, const void *src, size_t bytes) {
     HVN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     API_END
 }
+int hvn_pack_tables_dev(hvn_ctx *c, const int64_t *table, const int32_t *n_rows, int n, int max_rows, int64_t *packed,
+                        int64_t cap, int32_t *offs) {
+    API_BEGIN
+    use(c);
+    HVN_CHECK(table && n_rows && packed && offs && n >= 1 && max_rows >= 1 && cap >= 0, HVN_ERR_INVALID, "bad argument");
+    c->pp_launches += pack_tables(c->stream, (const long long *)table, n_rows, n, max_rows, (long long *)packed, cap, offs);
+    API_END
+}
+int hvn_get_stream(hvn_ctx *c, void **stream) {
+    API_BEGIN
+    HVN_CHECK(c && stream, HVN_ERR_INVALID, "null argument");
+    *stream = (void *)c->stream;
+    API_END
+}
 int hvn_sync(hvn_ctx *c) {
     API_BEGIN
     use(c);

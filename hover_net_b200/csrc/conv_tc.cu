@@ -125,7 +125,10 @@ struct TcGeom {
 };
 
 constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int XF_WARPS = 4;              // XF variant: warps 10..13 transform the A operand
+// XF variant: warps 10.. transform the A operand -- four (one per SM sub-partition) behind a BLOCK_N = 128 tile, eight
+// behind a BLOCK_N = 64 tile, whose K-slice leaves the tensor core in 570 instead of 800 cycles; with 576 threads the
+// register file allows 96 per thread, which the BLOCK_N = 128 epilogue does not fit in.
+template <int BLOCK_N> constexpr int xf_warps() { return BLOCK_N >= 128 ? 4 : 8; }
 constexpr int EP_WARPS = 8;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 
@@ -135,7 +138,7 @@ template <int BLOCK_N> __host__ __device__ constexpr int tc_stage_bytes() { retu
 // two-slot shared-memory ring one tile ahead (tm_a2_hi carries its tensor map), instead of by
 // per-thread global loads -- the thin residual layers are bound by how many bytes an SM keeps in flight.
 template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false, bool HALO = false>
-__global__ void __launch_bounds__(TC_THREADS + (XF ? XF_WARPS * 32 : 0), 1)
+__global__ void __launch_bounds__(TC_THREADS + (XF ? xf_warps<BLOCK_N>() * 32 : 0), 1)
 k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
           const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
@@ -159,6 +162,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     constexpr uint32_t RAW_TILE_BYTES = 128 * 64 * 4;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+    constexpr int XF_WARPS = xf_warps<BLOCK_N>();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // two accumulation buffers of 2*BLOCK_N columns: [hi*hi + lo*hi | hi*lo] (see the MMA issuer)
     constexpr uint32_t TMEM_COLS = 4 * BLOCK_N;
@@ -384,12 +388,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           }
         }
     } else if (XF && warp >= 2 + EP_WARPS) {
-        // ===================== A-operand transform (warps 10..13, XF only) =====================
-        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + 8*i: raw fp32 staging tile
-        // (row-major [128][64], filled by TMA) -> y = relu(x*scale+shift) -> fp16 hi/lo -> swizzled A tiles
+        // ===================== A-operand transform (warps 10..17, XF only) =====================
+        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + 16*i: raw fp32 staging tile
+        // (row-major [128][64], filled by TMA) -> y = relu(x*scale+shift) -> fp16 hi/lo -> swizzled A tiles.
+        // All eight row loads of a K-slice are issued before the first value is used: the loop used to be one
+        // LDS -> 30-instruction dependent chain -> STS per row (ncu/SASS: no two loads in flight), which paced the
+        // tensor core at roughly half its rate on every pre-activation 1x1 layer.
         const int t = threadIdx.x - (2 + EP_WARPS) * 32;
         const int l16 = t & 15, rg = t >> 4;
         const int wl = t & 31;
+        constexpr int XR = 128 / (XF_WARPS * 2);  // rows per thread
         uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
         const uint8_t *raw_gen = smem_raw + (raw_base - smem_u32(smem_raw));
         int it_global = 0;
@@ -400,23 +408,25 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 const int r = it_global & 1;
                 const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
                 const int c = kc * 64 + l16 * 4;
-                const bool cok = c < P.w.cin;
+                // channels past cin: TMA zero-fills the raw tile there and scale = shift = 0 keeps them 0 (zero weights
+                // must not meet Inf/NaN)
                 float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
-                if (cok) {
+                if (c < P.w.cin) {
                     sc = *reinterpret_cast<const float4 *>(P.in_scale + c);
                     sh = *reinterpret_cast<const float4 *>(P.in_shift + c);
                 }
                 mbar_wait(rfull_bar(r), rph);
+                const uint8_t *src = raw_gen + r * RAW_TILE_BYTES + rg * 256 + l16 * 16;
+                float4 v[XR];
+#pragma unroll
+                for (int i = 0; i < XR; ++i) v[i] = *reinterpret_cast<const float4 *>(src + i * (XF_WARPS * 2) * 256);
                 mbar_wait(empty_bar(s), ph ^ 1u);
-                const uint8_t *src = raw_gen + r * RAW_TILE_BYTES;
                 uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int row = rg + 8 * i;
-                    const float4 v = *reinterpret_cast<const float4 *>(src + row * 256 + l16 * 16);
-                    float y4[4] = {fmaxf(v.x * sc.x + sh.x, 0.f), fmaxf(v.y * sc.y + sh.y, 0.f),
-                                   fmaxf(v.z * sc.z + sh.z, 0.f), fmaxf(v.w * sc.w + sh.w, 0.f)};
-                    if (!cok) y4[0] = y4[1] = y4[2] = y4[3] = 0.f;  // channels past cin (zero weights) must stay finite
+#pragma unroll
+                for (int i = 0; i < XR; ++i) {
+                    const int row = rg + (XF_WARPS * 2) * i;
+                    float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
+                                   fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
                     uint2 oh, ol;
                     split4_f32<true>(y4, oh, ol);
                     // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
@@ -783,7 +793,7 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
     memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
     memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
     memcpy(&a2_hi, plan.tmap_a2_hi, 128); memcpy(&a2_lo, plan.tmap_a2_lo, 128);
-    k_conv_tc<BLOCK_N, STAGES, MODE, XF, RT><<<grid, TC_THREADS + (XF ? XF_WARPS * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
+    k_conv_tc<BLOCK_N, STAGES, MODE, XF, RT><<<grid, TC_THREADS + (XF ? xf_warps<BLOCK_N>() * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
 }
 
 constexpr int SMEM_LIMIT = 232448;

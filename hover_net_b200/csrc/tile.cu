@@ -54,7 +54,42 @@ __global__ void k_tile_scatter(const float *__restrict__ outs, int n, int step, 
     for (int c = 0; c < C; ++c) d[c] = s[c];
 }
 
+// Instance tables [n, max_rows, 10] (padded) -> packed rows [sum n_rows, 10] in map order + offs [n + 1].
+// One block per map: its offset is the sum of the earlier maps' row counts (n is a batch size: a strided sum).
+__global__ void k_pack_tables(const long long *__restrict__ table, const int *__restrict__ n_rows, int n, int max_rows,
+                              long long *__restrict__ packed, long long cap, int *__restrict__ offs) {
+    __shared__ int s_part[32];
+    __shared__ int s_off;
+    const int m = blockIdx.x;
+    int part = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) part += min(n_rows[i], max_rows);
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+        s_off = t;
+        offs[m] = t;
+        if (m == n - 1) offs[n] = t + min(n_rows[m], max_rows);
+    }
+    __syncthreads();
+    const int off = s_off, nr = min(n_rows[m], max_rows);
+    const long long *src = table + (size_t)m * max_rows * 10;
+    for (int i = threadIdx.x; i < nr * 10; i += blockDim.x) {
+        const long long row = off + i / 10;
+        if (row < cap) packed[(size_t)off * 10 + i] = src[i];
+    }
+}
+
 }  // namespace
+
+int pack_tables(cudaStream_t s, const long long *table, const int *n_rows, int n, int max_rows, long long *packed,
+                long long cap, int *offs) {
+    k_pack_tables<<<n, 256, 0, s>>>(table, n_rows, n, max_rows, packed, cap, offs);
+    HVN_CUDA(cudaGetLastError());
+    return 1;
+}
 
 void tile_grid(int H, int W, int patch_out, int *rows, int *cols) {
     auto steps = [&](int L) { return (L <= patch_out ? 0 : (L - patch_out + patch_out - 1) / patch_out) + 1; };

@@ -135,6 +135,16 @@ int hvn_infer_tile(hvn_ctx *ctx, const uint8_t *img_host, int H, int W, int patc
                    int32_t *inst_host, int64_t *table_host, int max_rows, int32_t *n_rows_host, int32_t *pts_host,
                    int64_t pts_cap, int32_t *offs_host);
 
+/* ---- end-of-batch gather support (replaces the reference's DataParallel gather, infer/base.py:69):
+ * hvn_pack_tables_dev compacts the padded tables of a batch, table_dev [n_maps,max_rows,10] + n_rows_dev [n_maps],
+ * into packed_dev [<= cap_rows,10] (map order, no padding) and offs_dev [n_maps + 1] int32 (row range of map m =
+ * [offs[m], offs[m+1]); offs[n_maps] = total; rows past cap_rows are not written) -- the buffer a rank hands to
+ * ncclAllGather.  hvn_get_stream returns the context's cudaStream_t so that a collective can be ordered after the
+ * library's kernels without a host synchronisation. */
+int hvn_pack_tables_dev(hvn_ctx *ctx, const int64_t *table_dev, const int32_t *n_rows_dev, int n_maps, int max_rows,
+                        int64_t *packed_dev, int64_t cap_rows, int32_t *offs_dev);
+int hvn_get_stream(hvn_ctx *ctx, void **cuda_stream);
+
 /* ---- device memory / stream helpers for callers without a CUDA binding of their own. */
 int hvn_malloc(hvn_ctx *ctx, size_t bytes, void **dev_ptr);
 int hvn_free(hvn_ctx *ctx, void *dev_ptr);
