@@ -3,8 +3,18 @@ once), and the only exchange is the end-of-batch gather of the variable-length i
 every rank -- the B200 replacement for the reference's single-process `torch.nn.DataParallel`
 scatter/gather (reference infer/base.py:69, run_infer.py:139).  Works on any torch.distributed
 backend (NCCL on the GPUs; gloo in the CPU tests)."""
-import torch
-import torch.distributed as dist
+try:  # torch is only needed for the multi-rank paths; single-GPU tile / WSI runs work without it
+    import torch
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    torch = dist = None
+
+
+def dist_info():
+    """(torch.distributed module or None, rank, world): world == 1 when torch is missing or no group is initialised."""
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
 
 
 def shard_range(n_items, rank, world):
@@ -17,7 +27,7 @@ def shard_range(n_items, rank, world):
 def gather_tables(table, nrows, group=None):
     """table [B,max_rows,10] int64, nrows [B] int32 (same B and max_rows on every rank) ->
     (table_all [world*B,max_rows,10], nrows_all [world*B]) on every rank, rank-major order."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    world = dist.get_world_size(group) if (dist is not None and dist.is_initialized()) else 1
     if world == 1:
         return table, nrows
     t_all = torch.empty((world * table.shape[0],) + tuple(table.shape[1:]), dtype=table.dtype, device=table.device)

@@ -30,8 +30,10 @@ class InferManager(object):
         if self.nr_types is not None and self.type_info_path is None:
             # the reference samples matplotlib's "hot" colormap at integer positions 0..nr_types-1, i.e.
             # its first entries (near-black reds); the same values without the matplotlib dependency
-            hot = [(10, 0, 0), (13, 0, 0), (15, 0, 0), (18, 0, 0), (21, 0, 0), (23, 0, 0), (26, 0, 0), (28, 0, 0)]
-            self.type_info_dict = {k: (str(k), hot[min(k, len(hot) - 1)]) for k in range(self.nr_types)}
+            # its first entries: red ramps linearly from 0.0416 at x = 0 to 1.0 at x = 0.365079 (x = k / 255), green and
+            # blue stay 0 there; `(cmap(k)[:3] * 255).astype(uint8)` truncates (reference infer/base.py:46-48)
+            hot = [(int((0.0416 + (1.0 - 0.0416) * (k / 255.0) / 0.365079) * 255), 0, 0) for k in range(self.nr_types)]
+            self.type_info_dict = {k: (str(k), hot[k]) for k in range(self.nr_types)}
         return
 
     def __load_model(self):

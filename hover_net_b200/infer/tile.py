@@ -60,12 +60,10 @@ def run_patches(padded, patch_info, win, run_step, batch_size):
     """Per-patch network outputs [n,h,w,C] for every row of patch_info, in patch_info order.
     Multi-GPU: rank r runs the contiguous shard `shard_range(n, r, world)`; shards are padded to equal
     length and exchanged with one all_gather (NCCL on device tensors, gloo in the CPU tests)."""
-    import torch.distributed as dist
-    from ..dist import shard_range
+    from ..dist import dist_info, shard_range
 
     n = patch_info.shape[0]
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
+    dist, rank, world = dist_info()
     lo, hi = shard_range(n, rank, world)
     outs = []
     for b0 in range(lo, hi, batch_size):
@@ -130,21 +128,22 @@ def _rm_n_mkdir(path):
 class InferManager(base.InferManager):
     """Run inference on tiles."""
 
-    def infer_image(self, img):
+    def infer_image(self, img, all_ranks=False):
         """RGB uint8 [H,W,3] -> (pred_map [H,W,C] float32, pred_inst int32 [H,W], inst_info_dict).
 
         Device path (a manager built by `InferManager(**method_args)`): reflect padding, patch extraction,
         stitching, cropping, `process` and the contours all run in libhvn (`hvn_infer_tile`); only the image
         goes up and the maps / instance table / contour points come back.  With torch.distributed initialised
         on NCCL (one process per GPU) each rank runs its contiguous slice of the patch grid into a zeroed
-        device map and the maps are summed with one all_reduce (disjoint supports: x + 0 is exact); the single
-        whole-map post-processing -- its min/max normalisations are global -- then runs on
-        every rank identically.  Host path (fake `run_step` in the CPU tests, gloo): `run_patches` + `_stitch`."""
-        import torch.distributed as dist
-        from ..dist import shard_range
+        device map and the maps are summed onto rank 0 with one NCCL reduce (disjoint supports: x + 0 is exact); the
+        single whole-map post-processing -- its min/max normalisations are global, so it cannot be
+        sharded bit-exactly -- then runs ONCE, on rank 0; the other ranks return (None, None, None).  `all_ranks=True`
+        all_reduces instead and post-processes everywhere (every rank gets the result; used by the 2-GPU parity test).
+        Host path (fake `run_step` in the CPU tests, gloo): `run_patches` + `_stitch`."""
+        from ..dist import dist_info, shard_range
         from ..models.hovernet.post_proc import table_to_dict
 
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        dist, rank, world = dist_info()
         win = int(self.patch_input_shape)
         if getattr(self, "device_tile_path", False) and (world == 1 or dist.get_backend() == "nccl"):
             ctx = self.net.ctx
@@ -160,7 +159,12 @@ class InferManager(base.InferManager):
             torch.cuda.synchronize()  # torch's stream -> the library's stream
             ctx.tile_predict_dev(d_img.data_ptr(), H, W, win, lo, hi, self.batch_size, d_pred.data_ptr())
             ctx.sync()
-            dist.all_reduce(d_pred)
+            if all_ranks:
+                dist.all_reduce(d_pred)
+            else:
+                dist.reduce(d_pred, dst=0)
+                if rank != 0:
+                    return None, None, None
             pred_map = d_pred.cpu().numpy()
         else:
             src_shape = img.shape
@@ -187,9 +191,9 @@ class InferManager(base.InferManager):
         file_path_list = glob.glob(patterning("%s/*" % self.input_dir))
         file_path_list.sort()  # ensure same order
         assert len(file_path_list) > 0, "Not Detected Any Files From Path"
-        import torch.distributed as dist
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        rank = dist.get_rank() if multi else 0
+        from ..dist import dist_info
+        dist, rank, world = dist_info()
+        multi = world > 1
         if rank == 0:  # every rank computes (the patch grid of each image is sharded); rank 0 alone writes
             for sub in ("json", "mat", "overlay"):
                 _rm_n_mkdir(self.output_dir + "/%s/" % sub)

@@ -8,6 +8,15 @@ from ... import _lib
 from ...arch import state_dict_spec
 
 
+def convert_pytorch_checkpoint(net_state_dict):
+    """reference run_utils/utils.py:15-29: a checkpoint saved from `DataParallel` has every key prefixed with
+    `module.`; the prefix is stripped only when ALL keys carry it."""
+    names = list(net_state_dict.keys())
+    if names and all(v.split(".")[0] == "module" for v in names):
+        net_state_dict = {".".join(k.split(".")[1:]): v for k, v in net_state_dict.items()}
+    return net_state_dict
+
+
 class HoVerNet(object):
     def __init__(self, input_ch=3, nr_types=None, freeze=False, mode="original", device=None):
         assert mode == "original" or mode == "fast", \
@@ -27,10 +36,7 @@ class HoVerNet(object):
     # ---- torch.nn.Module look-alikes used by reference infer/base.py:64-70
     def load_state_dict(self, state_dict, strict=True):
         spec = state_dict_spec(self.mode, self.nr_types)
-        sd = {}
-        for k, v in state_dict.items():
-            k = k[7:] if k.startswith("module.") else k  # run_utils/utils.py:15-29
-            sd[k] = v
+        sd = convert_pytorch_checkpoint(dict(state_dict))
         missing = [k for k in spec if k not in sd and not k.endswith("num_batches_tracked")
                    and k != "upsample2x.unpool_mat"]
         unexpected = [k for k in sd if k not in spec]

@@ -37,16 +37,19 @@ def _stub_imports():
     mpl.pyplot = types.ModuleType("matplotlib.pyplot")  # imported (unused on this path) at run_desc.py:2
     sys.modules.setdefault("matplotlib", mpl)
     sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
-    sk = types.ModuleType("skimage")
-    seg = types.ModuleType("skimage.segmentation")
+    try:  # the real function, when scikit-image is installed (oracle/regen_with_skimage.py) -- no stub then
+        import skimage.segmentation  # noqa: F401
+    except ImportError:
+        sk = types.ModuleType("skimage")
+        seg = types.ModuleType("skimage.segmentation")
 
-    def watershed(image, markers=None, mask=None):
-        return P.watershed(image, markers, mask)
+        def watershed(image, markers=None, mask=None):
+            return P.watershed(image, markers, mask)
 
-    seg.watershed = watershed
-    sk.segmentation = seg
-    sys.modules["skimage"] = sk
-    sys.modules["skimage.segmentation"] = seg
+        seg.watershed = watershed
+        sk.segmentation = seg
+        sys.modules["skimage"] = sk
+        sys.modules["skimage.segmentation"] = seg
     sys.path.insert(0, REF)
 
 

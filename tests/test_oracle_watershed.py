@@ -55,3 +55,84 @@ def test_invariants_on_synthetic_nuclei(oracle_pp):
         for c in range(1, n + 1):
             has_marker = (mk[comp == c] > 0).any()
             assert ((inst[comp == c] > 0).all()) == bool(has_marker)
+
+
+# ---- two independent restatements of SURVEY.md App. B must agree, ties included ------------------------------------
+def _rand_case(data_rng, h, w, quant):
+    from oracle.regen_with_skimage import random_case
+    return random_case(data_rng, h, w, quant)
+
+
+def test_two_restatements_agree_on_thousands_of_maps_including_marker_ties(oracle_pp):
+    """oracle/postproc_oracle.c (`hvo_watershed`) vs oracle/watershed_literal.py (pure Python, written separately
+    from SURVEY.md App. B): identical labels on hypothesis-generated maps -- random masks, 2..6 marker labels with
+    multi-pixel markers, and priorities quantised to 1 / 0.25 / continuous so that exact fp64 ties between age-0
+    marker pixels (the only place skimage's order is heap-layout dependent) are exercised heavily."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import watershed_literal as WL
+    seen = {"n": 0, "with_ties": 0}
+
+    @settings(max_examples=2500, deadline=None, derandomize=True)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(3, 26), st.integers(3, 26), st.sampled_from([0, 4, 1]))
+    def run(seed, h, w, quant):
+        image, markers, mask = _rand_case(np.random.default_rng(seed), h, w, quant)
+        ct = {}
+        a = oracle_pp.watershed(image, markers, mask)
+        b = WL.watershed(image, markers, mask, count_ties=ct)
+        assert np.array_equal(a, b)
+        seen["n"] += 1
+        seen["with_ties"] += ct["marker_ties"] > 0
+
+    run()
+    assert seen["n"] >= 2000 and seen["with_ties"] >= 500, seen
+
+
+def test_marker_tie_corner_case_is_measured():
+    """The declared corner case: the device floods order equal-priority age-0 marker pixels by raster
+    index, skimage by heap layout.  (a) On nuclei-like maps no two marker pixels of a map tie, so both orders give
+    the same labels; (b) on maps with injected exact ties the two orders DO differ in a measurable fraction of
+    cases -- one tie between two differently-labelled marker pixels next to a shared unlabelled pixel is enough
+    (ADVICE r1), no second tie is needed."""
+    from oracle import postproc_oracle as P
+    from oracle import watershed_literal as WL
+    P.build()
+    for seed in range(3):
+        pm = synth.synth_pred_map(100, 100, None, seed)
+        _, stg = P.proc_np_hv(pm, True)
+        ct = {}
+        heap = WL.watershed(stg["dist"], stg["marker"], stg["blb"], count_ties=ct)
+        rast = WL.watershed(stg["dist"], stg["marker"], stg["blb"], tie_break="raster")
+        assert ct["marker_ties"] == 0 and np.array_equal(heap, rast)
+        assert np.array_equal(heap, P.watershed(stg["dist"], stg["marker"], stg["blb"]))
+    rng = np.random.default_rng(7)
+    tied = differ = 0
+    for i in range(400):
+        image, markers, mask = _rand_case(rng, int(rng.integers(4, 30)), int(rng.integers(4, 30)), (4, 1)[i % 2])
+        ct = {}
+        heap = WL.watershed(image, markers, mask, count_ties=ct)
+        if ct["marker_ties"] == 0:
+            continue
+        tied += 1
+        differ += not np.array_equal(heap, WL.watershed(image, markers, mask, tie_break="raster"))
+    assert tied > 100 and 0 < differ < tied   # measured here: roughly one tied map in ten changes a label
+    # minimal witness: three equal-priority marker pixels [1, 1, ., 2] -- after the first pop the heap moves its LAST
+    # entry (label 2) to the root, so label 2 reaches the free pixel before the second label-1 pixel does
+    img = np.zeros((1, 4))
+    mk = np.array([[1, 1, 0, 2]], np.int32)
+    one = np.ones((1, 4), np.int32)
+    assert WL.watershed(img, mk, one).tolist() == [[1, 1, 2, 2]]
+    assert WL.watershed(img, mk, one, tie_break="raster").tolist() == [[1, 1, 1, 2]]
+    assert P.watershed(img, mk, one).tolist() == [[1, 1, 2, 2]]
+
+
+def test_real_skimage_when_available(oracle_pp):
+    """Runs only where scikit-image is installed (not in the build image): the pin itself."""
+    import pytest
+    sk = pytest.importorskip("skimage.segmentation")
+    from oracle import watershed_literal as WL
+    rng = np.random.default_rng(0)
+    for i in range(300):
+        image, markers, mask = _rand_case(rng, int(rng.integers(4, 40)), int(rng.integers(4, 40)), (0, 4, 1)[i % 3])
+        ref = sk.watershed(image, markers=markers, mask=mask)
+        assert np.array_equal(ref, oracle_pp.watershed(image, markers, mask))
+        assert np.array_equal(ref, WL.watershed(image, markers, mask))

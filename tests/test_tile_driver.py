@@ -181,7 +181,7 @@ def _two_rank_tile_worker(rank, world, port, out):
     mgr = InferManager(method={"model_args": {"nr_types": nt, "mode": mode, "device": rank},
                                "model_path": synth.make_state_dict(mode, nt, seed=0)}, type_info_path=None)
     mgr.patch_input_shape, mgr.patch_output_shape, mgr.batch_size = 256, 164, 4
-    pred, inst, info = mgr.infer_image(img)                       # patch grid sharded over the ranks + all_reduce
+    pred, inst, info = mgr.infer_image(img, all_ranks=True)       # patch grid sharded over the ranks + all_reduce
     one = mgr.net.ctx.infer_tile(img, 256, 4)                     # the same image on this rank alone
     ok = bool(np.array_equal(pred, one[0]) and np.array_equal(inst, one[1]) and len(info) > 0)
     flags = [None] * world

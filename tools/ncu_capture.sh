@@ -1,13 +1,14 @@
 #!/bin/bash
 # ncu --set full captures of single conv_tc instantiations (one launch each) on tools/ncu_target.py.
-#   tools/ncu_capture.sh <tag> <batch> "<BLOCK_N> <STAGES> <MODE> <XF> <RT> <HALO> <skip> <name>" ...
-tag=$1; batch=$2; shift 2
+#   tools/ncu_capture.sh <tag> <batch> <mode> "<BLOCK_N> <STAGES> <MODE> <XF> <RT> <HALO> <skip> <name>" ...
+# <skip> = matching launches to skip (the warm-up pass launches each instantiation as often as the profiled pass).
+tag=$1; batch=$2; mode=$3; shift 3
 mkdir -p gpurun_out
 for spec in "$@"; do
   set -- $spec
   pat="k_conv_tc<\\(int\\)$1, \\(int\\)$2, \\(int\\)$3, \\(bool\\)$4, \\(bool\\)$5, \\(bool\\)$6>"
-  timeout 240 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k "regex:$pat" -s $7 -c 1 -f -o gpurun_out/${tag}_conv_tc_$8 python tools/ncu_target.py $batch > gpurun_out/ncu_$8.log 2>&1
-  echo "$8 rc=$? $(grep -c '==PROF==' gpurun_out/ncu_$8.log) prof lines"
+  timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+      -k "regex:$pat" -s $7 -c 1 -f -o gpurun_out/${tag}_conv_tc_$8 python tools/ncu_target.py $batch $mode > gpurun_out/ncu_${tag}_$8.log 2>&1
+  echo "$8 rc=$? $(grep -c '==PROF==' gpurun_out/ncu_${tag}_$8.log) prof lines"
 done
-ls -la gpurun_out/*.ncu-rep 2>/dev/null
+ls -la gpurun_out/${tag}_*.ncu-rep 2>/dev/null
