@@ -112,6 +112,18 @@ class Context:
         check(lib().hvn_out_shape(self._h, int(h), int(w), ctypes.byref(oh), ctypes.byref(ow), ctypes.byref(oc)))
         return oh.value, ow.value, oc.value
 
+    def _retry_range(self, call):
+        """Runs call() -> rc.  HVN_ERR_RANGE (-6: an activation outside the fp16 hi+lo range) is answered by raising
+        the exact power-of-two activation scale (option "act_shift", +6 per attempt) and running again -- the result
+        is never a silently clamped map.  The shift is kept for later calls."""
+        rc = call()
+        tries = 0
+        while rc == -6 and tries < 6:
+            tries += 1
+            self.set_option("act_shift", self.counter("act_shift") + 6)
+            rc = call()
+        return rc
+
     # ---- host-buffer entry points (what the reference-facing plugin calls)
     def forward(self, imgs_u8, out=None):
         x = np.ascontiguousarray(imgs_u8, dtype=np.uint8)
@@ -120,7 +132,7 @@ class Context:
         oh, ow, oc = self.out_shape(H, W)
         if out is None:
             out = np.empty((B, oh, ow, oc), dtype=np.float32)
-        check(lib().hvn_forward(self._h, _ptr(x), B, H, W, _ptr(out)))
+        check(self._retry_range(lambda: lib().hvn_forward(self._h, _ptr(x), B, H, W, _ptr(out))))
         return out
 
     def postproc(self, pred, nr_types=None, max_rows=None):
@@ -208,8 +220,9 @@ class Context:
             nrows = np.zeros((1,), dtype=np.int32)
             offs = np.zeros((max_rows + 1,), dtype=np.int32) if contours else None
             pts = np.empty((pts_cap, 2), dtype=np.int32) if contours else None
-            rc = L.hvn_infer_tile(self._h, _ptr(x), H, W, int(patch_in), int(batch), _ptr(pred), _ptr(inst), _ptr(table),
-                                  int(max_rows), _ptr(nrows), _ptr(pts), int(pts_cap if contours else 0), _ptr(offs))
+            rc = self._retry_range(lambda: L.hvn_infer_tile(
+                self._h, _ptr(x), H, W, int(patch_in), int(batch), _ptr(pred), _ptr(inst), _ptr(table), int(max_rows),
+                _ptr(nrows), _ptr(pts), int(pts_cap if contours else 0), _ptr(offs)))
             if rc == -4:
                 if int(nrows[0]) > max_rows:
                     max_rows = int(nrows[0])
@@ -239,8 +252,8 @@ class Context:
             inst = np.empty((B, oh, ow), dtype=np.int32)
             table = np.zeros((B, max_rows, ROW_LEN), dtype=np.int64)
             nrows = np.zeros((B,), dtype=np.int32)
-            rc = lib().hvn_forward_postproc(self._h, _ptr(x), B, H, W, _ptr(pred), _ptr(inst), _ptr(table),
-                                            int(max_rows), _ptr(nrows))
+            rc = self._retry_range(lambda: lib().hvn_forward_postproc(self._h, _ptr(x), B, H, W, _ptr(pred), _ptr(inst),
+                                                                      _ptr(table), int(max_rows), _ptr(nrows)))
             if rc == -4:
                 max_rows = int(nrows.max())
                 continue

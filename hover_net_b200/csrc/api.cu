@@ -36,6 +36,16 @@ struct hvn_ctx {
     catch (const std::exception &e) { g_err = e.what(); return HVN_ERR_INVALID; } \
     return HVN_OK;
 
+// After the context stream has been synchronised: a raised range flag becomes HVN_ERR_RANGE (once), never a silently
+// clamped result.
+static void check_range(hvn_ctx *c) {
+    if (c->model && c->model->range_overflow()) {
+        c->model->reset_range_flag(c->stream);
+        throw Error(HVN_ERR_RANGE, "an activation exceeded the fp16-split range (|x| > 65504 * 2^act_shift, act_shift = " +
+                                       std::to_string(c->model->act_shift) + "); set option \"act_shift\" higher and run again");
+    }
+}
+
 static void use(hvn_ctx *c) {
     HVN_CHECK(c != nullptr, HVN_ERR_INVALID, "null context");
     HVN_CUDA(cudaSetDevice(c->device));
@@ -129,6 +139,15 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "tc_seg_chunks") tc_set_seg_chunks((int)value);
     else if (k == "tc_block_n") tc_set_block_n((int)value);
     else if (k == "tc_res_tma") tc_set_res_tma((int)value);
+    else if (k == "act_shift") {
+        HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");
+        HVN_CHECK(value >= 0 && value <= 48, HVN_ERR_INVALID, "act_shift out of range (0..48)");
+        if (c->model->act_shift != (int)value) {
+            HVN_CUDA(cudaStreamSynchronize(c->stream));
+            c->model->act_shift = (int)value;
+            if (c->model->finalized) c->model->finalize();  // re-derives the BN shifts / head weights; plans are rebuilt
+        }
+    }
     else if (k == "tc_halo") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->tc_halo = (int)value; }
     else if (k == "profile") { c->profile = (int)value; if (c->model) c->model->profile_ops = value >= 3 ? 2 : (value >= 2 ? 1 : 0); }
     else throw Error(HVN_ERR_INVALID, "unknown option " + k);
@@ -138,6 +157,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
 int64_t hvn_get_counter(const hvn_ctx *c, const char *key) {
     if (!c || !key) return -1;
     std::string k = key;
+    if (k == "act_shift") return c->model ? c->model->act_shift : 0;
     if (k == "kernel_launches") return (c->model ? c->model->kernel_launches : 0) + c->pp_launches;
     if (k == "tc_launches") return c->model ? c->model->tc_launches : 0;
     if (k == "pp_launches") return c->pp_launches;
@@ -222,6 +242,7 @@ int hvn_forward(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, float *out
     HVN_CUDA(cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, c->stream));
     HVN_CUDA(cudaStreamSynchronize(c->stream));
     finish_profile(c, true, false);
+    check_range(c);
     API_END
 }
 
@@ -353,6 +374,7 @@ int hvn_forward_postproc(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, f
     HVN_CUDA(cudaMemcpyAsync(table, d_tab, tb * 8, cudaMemcpyDeviceToHost, c->stream));
     HVN_CUDA(cudaStreamSynchronize(c->stream));
     finish_profile(c, true, true);
+    check_range(c);
     check_rows(n_rows, B, max_rows);
     API_END
 }
@@ -424,6 +446,7 @@ int hvn_infer_tile(hvn_ctx *c, const uint8_t *img, int H, int W, int patch_in, i
     if (offs) HVN_CUDA(cudaMemcpyAsync(offs, d_offs, no * 4, cudaMemcpyDeviceToHost, c->stream));
     HVN_CUDA(cudaStreamSynchronize(c->stream));
     finish_profile(c, true, true);
+    check_range(c);
     check_rows(n_rows, 1, max_rows);
     if (offs) {
         const long long total = offs[no - 1];
@@ -493,6 +516,7 @@ int hvn_sync(hvn_ctx *c) {
     API_BEGIN
     use(c);
     HVN_CUDA(cudaStreamSynchronize(c->stream));
+    check_range(c);
     API_END
 }
 int hvn_timer_start(hvn_ctx *c) {
@@ -508,6 +532,7 @@ int hvn_timer_stop(hvn_ctx *c, float *ms) {
     HVN_CUDA(cudaEventRecord(c->tev[1], c->stream));
     HVN_CUDA(cudaEventSynchronize(c->tev[1]));
     HVN_CUDA(cudaEventElapsedTime(ms, c->tev[0], c->tev[1]));
+    check_range(c);
     API_END
 }
 int hvn_stage_ms(const hvn_ctx *c, const char *name, float *ms) {

@@ -108,6 +108,8 @@ Model::~Model() {
     for (auto &e : ev_join_) if (e) cudaEventDestroy(e);
     plans_.clear();
     for (void *p : wallocs_) cudaFree(p);
+    if (d_flag_) cudaFree(d_flag_);
+    if (h_flag_) cudaFreeHost(h_flag_);
 }
 
 void Model::load(const std::string &name_in, const float *data, int ndim, const int64_t *shape) {
@@ -133,6 +135,15 @@ const std::vector<float> &Model::hostp(const std::string &name) const {
     return it->second;
 }
 
+// Exponent e with max|w| * 2^e in [2^13, 2^14): see ConvWeights::oscale.  Inf / NaN weights are a checkpoint error.
+static int weight_exponent(float mx) {
+    HVN_CHECK(std::isfinite(mx), -3, "non-finite convolution weight in the checkpoint");
+    if (mx == 0.f) return 0;
+    int ex = 0;
+    std::frexp(mx, &ex);  // mx = m * 2^ex, m in [0.5, 1)  ->  mx in [2^(ex-1), 2^ex)
+    return 14 - ex;
+}
+
 // OIHW fp32 -> [tap][cout][cin_pad] split fp16 (grouped convs become block-diagonal dense)
 void Model::make_conv(const std::string &name, int groups) {
     const ParamSpec &s = spec[index.at(name)];
@@ -144,11 +155,16 @@ void Model::make_conv(const std::string &name, int groups) {
     cw.cin_pad = (cin + 63) / 64 * 64;
     size_t n = (size_t)cw.taps * O * cw.cin_pad;
     std::vector<__half> hi(n, __float2half_rn(0.f)), lo(n, __float2half_rn(0.f));
+    std::vector<float> osc(O, 1.f);
     for (int o = 0; o < O; ++o) {
         int g = o / og;
+        float mx = 0.f;
+        for (size_t j = 0; j < (size_t)I * cw.taps; ++j) mx = std::max(mx, std::fabs(w[(size_t)o * I * cw.taps + j]));
+        const int e = weight_exponent(mx);
+        osc[o] = std::ldexp(1.f, -e);
         for (int i = 0; i < I; ++i)
             for (int t = 0; t < cw.taps; ++t) {
-                float v = w[((size_t)o * I + i) * cw.taps + t];
+                float v = std::ldexp(w[((size_t)o * I + i) * cw.taps + t], e);
                 __half h = __float2half_rn(v);
                 __half l = __float2half_rn(v - __half2float(h));
                 size_t d = ((size_t)t * O + o) * cw.cin_pad + (size_t)g * I + i;
@@ -160,6 +176,9 @@ void Model::make_conv(const std::string &name, int groups) {
     cw.lo = dalloc<__half>(n, wallocs_, false);
     HVN_CUDA(cudaMemcpy(cw.hi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
     HVN_CUDA(cudaMemcpy(cw.lo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    float *d_osc = dalloc<float>(O, wallocs_, false);
+    HVN_CUDA(cudaMemcpy(d_osc, osc.data(), O * sizeof(float), cudaMemcpyHostToDevice));
+    cw.oscale = d_osc;
     conv_[name] = cw;
 }
 
@@ -174,13 +193,20 @@ void Model::make_conv_concat(const std::string &key, const std::string &name1, c
     cw.taps = 1; cw.kh = cw.kw = 1; cw.cout = O; cw.cin = I1 + I2; cw.cin_pad = I1 + I2;
     size_t n = (size_t)O * cw.cin_pad;
     std::vector<__half> hi(n), lo(n);
-    for (int o = 0; o < O; ++o)
+    std::vector<float> osc(O, 1.f);
+    for (int o = 0; o < O; ++o) {
+        float mx = 0.f;
+        for (int i = 0; i < I1; ++i) mx = std::max(mx, std::fabs(w1[(size_t)o * I1 + i]));
+        for (int i = 0; i < I2; ++i) mx = std::max(mx, std::fabs(w2[(size_t)o * I2 + i]));
+        const int e = weight_exponent(mx);  // one exponent per output channel: both sources accumulate into it
+        osc[o] = std::ldexp(1.f, -e);
         for (int i = 0; i < I1 + I2; ++i) {
-            float v = i < I1 ? w1[(size_t)o * I1 + i] : w2[(size_t)o * I2 + (i - I1)];
+            float v = std::ldexp(i < I1 ? w1[(size_t)o * I1 + i] : w2[(size_t)o * I2 + (i - I1)], e);
             __half h = __float2half_rn(v);
             hi[(size_t)o * cw.cin_pad + i] = h;
             lo[(size_t)o * cw.cin_pad + i] = __float2half_rn(v - __half2float(h));
         }
+    }
     cw.hi = dalloc<__half>(n, wallocs_, false);
     cw.lo = dalloc<__half>(n, wallocs_, false);
     HVN_CUDA(cudaMemcpy(cw.hi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
@@ -198,6 +224,10 @@ void Model::make_bn(const std::string &p) {
         double s = (double)g[i] / std::sqrt((double)v[i] + 1e-5);
         sc[i] = (float)s;
         sh[i] = (float)((double)b[i] - (double)m[i] * s);
+        // act_shift: activations are stored as x * 2^-s.  A BN whose input is already scaled keeps its scale and
+        // shrinks its shift; the stem's BN sees the unscaled image and shrinks both.  (ldexp: exact.)
+        sh[i] = std::ldexp(sh[i], -act_shift);
+        if (p == "conv0.bn") sc[i] = std::ldexp(sc[i], -act_shift);
     }
     BNParams bp;
     bp.c = c;
@@ -206,6 +236,11 @@ void Model::make_bn(const std::string &p) {
     HVN_CUDA(cudaMemcpy(bp.scale, sc.data(), c * 4, cudaMemcpyHostToDevice));
     HVN_CUDA(cudaMemcpy(bp.shift, sh.data(), c * 4, cudaMemcpyHostToDevice));
     bn_[p] = bp;
+}
+
+void Model::reset_range_flag(cudaStream_t s) {
+    if (d_flag_) HVN_CUDA(cudaMemsetAsync(d_flag_, 0, sizeof(unsigned int), s));
+    if (h_flag_) *h_flag_ = 0;
 }
 
 void Model::finalize() {
@@ -217,6 +252,13 @@ void Model::finalize() {
     for (void *p : wallocs_) cudaFree(p);
     wallocs_.clear();
     conv_.clear(); bn_.clear(); head_w_.clear(); head_b_.clear();
+    HVN_CHECK(act_shift >= 0 && act_shift <= 48, -1, "act_shift out of range (0..48)");
+    if (!d_flag_) {
+        HVN_CUDA(cudaMalloc((void **)&d_flag_, sizeof(unsigned int)));
+        HVN_CUDA(cudaMemset(d_flag_, 0, sizeof(unsigned int)));
+        HVN_CUDA(cudaMallocHost((void **)&h_flag_, sizeof(unsigned int)));
+        *h_flag_ = 0;
+    }
     for (auto &s : spec) {
         if (s.ignored) continue;
         const std::string &n = s.name;
@@ -231,7 +273,8 @@ void Model::finalize() {
             conv0_w_ = dalloc<float>(t.size(), wallocs_, false);
             HVN_CUDA(cudaMemcpy(conv0_w_, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
         } else if (n.size() > 15 && n.compare(n.size() - 15, 15, ".u0.conv.weight") == 0) {
-            const auto &w = hostp(n);
+            std::vector<float> w = hostp(n);
+            for (auto &x : w) x = std::ldexp(x, act_shift);  // the heads see features scaled by 2^-act_shift
             float *d = dalloc<float>(w.size(), wallocs_, false);
             HVN_CUDA(cudaMemcpy(d, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
             head_w_[n.substr(0, n.size() - 7)] = d;
@@ -392,6 +435,7 @@ Plan &Model::plan(int B, int H, int W) {
         r.lo = dalloc<__half>(n, P.allocs, true);
         P.bytes += 2 * n * sizeof(__half);
         r.sN = (long long)h * w * c; r.sH = w * c; r.sW = c; r.h = h; r.w = w; r.c = c;
+        r.flag = d_flag_;
         return r;
     };
     auto new_raw = [&](int h, int w, int c) {
@@ -615,6 +659,7 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
     if (profile_ops) { class_ms.clear(); class_flops.clear(); class_launches.clear(); }
     last_flops = 0;
     if (conv_path == 2 || profile_ops >= 2) debug_log.clear();
+
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int bc = std::min(chunk, B - b0);
         Plan &P = plan(bc, H, W);
@@ -683,6 +728,7 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
         }
     }
     s = main_stream;
+    HVN_CUDA(cudaMemcpyAsync(h_flag_, d_flag_, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     HVN_CUDA(cudaGetLastError());
     if (profile_ops) {
         HVN_CUDA(cudaStreamSynchronize(s));

@@ -69,6 +69,14 @@ class Model {
     int xform = 1;           // fuse pre-activation BN+ReLU into the consuming 1x1 conv's A-operand load
     int branch_streams = 1;  // run the decoder branches on separate streams
     int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only, 2 auto + per-layer self test
+    // Activations travel as fp16 hi + lo, finite up to 65504.  act_shift = s stores every activation as x * 2^-s:
+    // the stem's BN scale, every BN shift and (inversely) the head weights absorb the factor, so the network function
+    // is unchanged (powers of two are exact) while the representable range grows to 65504 * 2^s.  0 by default; raise
+    // it when a forward reports HVN_ERR_RANGE (the Python binding retries with +6 automatically).
+    int act_shift = 0;
+    // true if the last forward() stored a value outside the fp16 range (valid after the stream was synchronised)
+    bool range_overflow() const { return h_flag_ && *h_flag_ != 0; }
+    void reset_range_flag(cudaStream_t s);  // after the host has seen (and reported) an overflow
 
     void load(const std::string &name, const float *data, int ndim, const int64_t *shape);
     void finalize();
@@ -95,6 +103,8 @@ class Model {
     std::vector<void *> wallocs_;
     std::map<std::string, std::unique_ptr<Plan>> plans_;
     std::vector<std::string> branches_;
+    unsigned int *d_flag_ = nullptr;          // device range flag (raised by split stores)
+    unsigned int *h_flag_ = nullptr;          // pinned host copy, refreshed at the end of every forward()
     cudaStream_t side_[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork_ = nullptr, ev_join_[2] = {nullptr, nullptr};
     void add_spec(const std::string &name, std::initializer_list<int64_t> shape, bool ignored = false);

@@ -6,7 +6,8 @@
 
 namespace hvn {
 
-__device__ __forceinline__ void split_f32(float x, __half &hi, __half &lo) {
+__device__ __forceinline__ void split_f32(float x, __half &hi, __half &lo, unsigned int *flag = nullptr) {
+    if (flag && fabsf(x) > 65504.f) *flag = 1u;  // benign race: every writer stores the same value
     x = fminf(fmaxf(x, -65504.f), 65504.f);
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
@@ -17,7 +18,12 @@ __device__ __forceinline__ float join_f16(__half hi, __half lo) { return __half2
 // Four values at once with the packed conversions (one F2FP per pair): same roundings as split_f32.
 // NONNEG: the inputs are already >= 0 (post-ReLU), so only the upper clamp is needed.
 template <bool NONNEG = false>
-__device__ __forceinline__ void split4_f32(const float t[4], uint2 &hi, uint2 &lo) {
+__device__ __forceinline__ void split4_f32(const float t[4], uint2 &hi, uint2 &lo, unsigned int *flag = nullptr) {
+    if (flag) {
+        const float m = NONNEG ? fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]))
+                               : fmaxf(fmaxf(fabsf(t[0]), fabsf(t[1])), fmaxf(fabsf(t[2]), fabsf(t[3])));
+        if (m > 65504.f) *flag = 1u;
+    }
     float x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) x[i] = NONNEG ? fminf(t[i], 65504.f) : fminf(fmaxf(t[i], -65504.f), 65504.f);
@@ -30,6 +36,10 @@ __device__ __forceinline__ void split4_f32(const float t[4], uint2 &hi, uint2 &l
 
 // 4 consecutive output channels c..c+3 of output pixel (n, oy, ox); c % 4 == 0.
 __device__ __forceinline__ void conv_epilogue4(const ConvParams &P, int n, int oy, int ox, int c, float v[4]) {
+    if (P.w.oscale) {  // undo the per-channel power-of-two weight exponent (exact)
+        const float4 ws = *reinterpret_cast<const float4 *>(P.w.oscale + c);
+        v[0] *= ws.x; v[1] *= ws.y; v[2] *= ws.z; v[3] *= ws.w;
+    }
     if (P.res.p) {
         const float4 r = *reinterpret_cast<const float4 *>(P.res.p + n * P.res.sN + (long long)oy * P.res.sH +
                                                            (long long)ox * P.res.sW + c);
@@ -52,7 +62,7 @@ __device__ __forceinline__ void conv_epilogue4(const ConvParams &P, int n, int o
                           v[2] + join_f16(h23.x, l23.x), v[3] + join_f16(h23.y, l23.y)};
             __half oh[4], ol[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i]);
+            for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i], P.out_split.flag);
             *reinterpret_cast<uint2 *>(P.out_split.hi + oo) = *reinterpret_cast<uint2 *>(oh);
             *reinterpret_cast<uint2 *>(P.out_split.lo + oo) = *reinterpret_cast<uint2 *>(ol);
         }
@@ -69,7 +79,7 @@ __device__ __forceinline__ void conv_epilogue4(const ConvParams &P, int n, int o
         }
         __half oh[4], ol[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i]);
+        for (int i = 0; i < 4; ++i) split_f32(t[i], oh[i], ol[i], P.out_split.flag);
         long long oo = n * P.out_split.sN + (long long)oy * P.out_split.sH + (long long)ox * P.out_split.sW + c;
         *reinterpret_cast<uint2 *>(P.out_split.hi + oo) = *reinterpret_cast<uint2 *>(oh);
         *reinterpret_cast<uint2 *>(P.out_split.lo + oo) = *reinterpret_cast<uint2 *>(ol);
@@ -104,16 +114,18 @@ __device__ __forceinline__ void epi_prefetch(const ConvParams &P, int n, int oy,
 
 __device__ __forceinline__ void store_split4(const SplitRef &o, long long off, const float t[4]) {
     uint2 oh, ol;
-    split4_f32(t, oh, ol);
+    split4_f32(t, oh, ol, o.flag);
     *reinterpret_cast<uint2 *>(o.hi + off) = oh;
     *reinterpret_cast<uint2 *>(o.lo + off) = ol;
 }
 
 // sc / sh: the BN scale / shift of channels c..c+3, loaded once per tile by the caller (they do not depend
 // on the pixel; loading them per store left the write-out loop waiting on global loads).
+// ws: 2^-e of the four channels (ConvWeights::oscale), applied to the accumulator first.
 template <int MODE>
 __device__ __forceinline__ void epi_finish(const ConvParams &P, int n, int oy, int ox, int c, float v[4],
-                                           const EpiPre<MODE> &pre, const float4 &s, const float4 &b) {
+                                           const EpiPre<MODE> &pre, const float4 &s, const float4 &b, const float4 &ws) {
+    v[0] *= ws.x; v[1] *= ws.y; v[2] *= ws.z; v[3] *= ws.w;
     if constexpr (MODE == EPI_RES) { v[0] += pre.r.x; v[1] += pre.r.y; v[2] += pre.r.z; v[3] += pre.r.w; }
     if (P.out_raw.p) {
         float *o = P.out_raw.p + n * P.out_raw.sN + (long long)oy * P.out_raw.sH + (long long)ox * P.out_raw.sW + c;

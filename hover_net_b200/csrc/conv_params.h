@@ -13,6 +13,10 @@ struct SplitRef {            // view into a split NHWC buffer, already offset to
     long long sN = 0;        // element strides
     int sH = 0, sW = 0;
     int h = 0, w = 0, c = 0; // view extent
+    // Range guard: a value outside fp16's finite range (|x| > 65504) cannot be stored as hi + lo.  Every store into a
+    // split tensor checks it and raises this device flag (the stored value is clamped so that everything downstream
+    // stays finite); the host turns a raised flag into HVN_ERR_RANGE instead of returning a silently clamped result.
+    unsigned int *flag = nullptr;
 };
 struct RawRef {              // view into a raw fp32 NHWC buffer
     float *p = nullptr;
@@ -23,6 +27,12 @@ struct RawRef {              // view into a raw fp32 NHWC buffer
 
 struct ConvWeights {         // [tap][cout][cin_pad] fp16 hi/lo, K-major per tap; cin_pad % 64 == 0
     __half *hi = nullptr, *lo = nullptr;
+    // Per-output-channel power-of-two exponent: the stored planes hold w * 2^e[cout] with e chosen so that the largest
+    // |w| of the channel lies in [2^13, 2^14) -- both planes then stay in fp16's NORMAL range for every weight down
+    // to 2^-17 of the channel's maximum (an unscaled |w| < 2^-3 would leave `lo` subnormal, i.e. fewer than the 22
+    // bits the split promises; |w| < 6e-8 would vanish).  oscale[cout] = 2^-e is applied to the fp32 accumulator in
+    // the epilogue; scaling by powers of two is exact, so results do not depend on e.
+    const float *oscale = nullptr;
     int taps = 0, cout = 0, cin = 0, cin_pad = 0, kh = 0, kw = 0;
 };
 

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) k_bnrelu(RawRef in, int B, const float *_
                        fmaxf(v.w * s.w + b.w, 0.f)};
         __half oh[4], ol[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) split_f32(tt[k], oh[k], ol[k]);
+        for (int k = 0; k < 4; ++k) split_f32(tt[k], oh[k], ol[k], out.flag);
         long long oo = n * out.sN + (long long)y * out.sH + (long long)x * out.sW + c;
         *reinterpret_cast<uint2 *>(out.hi + oo) = *reinterpret_cast<uint2 *>(oh);
         *reinterpret_cast<uint2 *>(out.lo + oo) = *reinterpret_cast<uint2 *>(ol);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) k_up2_add(RawRef in, int B, SplitRef skip
         const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         __half oh8[8], ol8[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) split_f32(v[k] + join_f16(hh[k], ll[k]), oh8[k], ol8[k]);
+        for (int k = 0; k < 8; ++k) split_f32(v[k] + join_f16(hh[k], ll[k]), oh8[k], ol8[k], out.flag);
         const long long oo = n * out.sN + (long long)Y * out.sH + (long long)X * out.sW + c;
         *reinterpret_cast<uint4 *>(out.hi + oo) = *reinterpret_cast<uint4 *>(oh8);
         *reinterpret_cast<uint4 *>(out.lo + oo) = *reinterpret_cast<uint4 *>(ol8);

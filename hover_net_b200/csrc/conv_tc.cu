@@ -157,6 +157,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     // XF only: raw_full[2], raw_empty[2] barriers and a 2-slot ring of raw fp32 [128][64] staging tiles
     auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * r; };
     auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * (2 + r); };
+    // XF: one "raw tile + weights landed" barrier per stage (same four slots; STAGES <= 4)
+    auto xfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * s; };
+    static_assert(!XF || STAGES <= 4, "XF: at most four stages (barrier slots)");
     const uint32_t ep_base = bar_base + 8u * (2 * STAGES + 4) + 48u;  // 8 warps x [32][32] fp32 transpose tiles (XOR-swizzled)
     const uint32_t raw_base = (ep_base + EP_WARPS * 4096u + 1023u) & ~1023u;
     constexpr uint32_t RAW_TILE_BYTES = 128 * 64 * 4;
@@ -168,9 +171,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     constexpr uint32_t TMEM_COLS = 4 * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
-        if (XF || RT) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), XF ? XF_WARPS : EP_WARPS); }
+        if (XF) for (int s = 0; s < STAGES; ++s) mbar_init(xfull_bar(s), 1);
+        if (RT) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), EP_WARPS); }
         if (HALO) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), 1); }  // halo slots: full / empty
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -186,7 +190,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     const int total_tiles = G.tiles_m * G.tiles_n;
     const int taps = P.w.taps;
     const int kiters = taps * G.kchunks;
-    const uint32_t tx_bytes = (uint32_t)((XF ? 0 : 2 * (G.flat ? 128 : G.bw * G.bh) * 128) + 2 * BLOCK_N * 128);
+    const uint32_t tx_bytes = (uint32_t)(2 * (G.flat ? 128 : G.bw * G.bh) * 128 + 2 * BLOCK_N * 128);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -257,25 +261,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     ++tile_count;
                 }
                 for (int it = 0; it < kiters; ++it, ++it_global) {
-                    if constexpr (XF) {  // raw fp32 A tile of this K-slice -> staging ring (tm_a_hi is the fp32 map)
-                        const int r = it_global & 1;
-                        const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
-                        mbar_wait(rempty_bar(r), rph ^ 1u);
-                        mbar_expect_tx(rfull_bar(r), (uint32_t)((G.flat ? 128 : G.bw * G.bh) * 256));
-                        if (G.flat) tma_2d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), it * 64, (int)m0);
-                        else tma_4d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), it * 64, x0, y0, n_img);
-                    }
                     const int s = it_global % STAGES;
                     const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = smem_base + s * STAGE_BYTES;
                     const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES, b_hi = sa + 2 * A_TILE_BYTES,
                                    b_lo = b_hi + BLOCK_N * 128;
-                    mbar_expect_tx(full_bar(s), tx_bytes);
                     const int tap = it / G.kchunks, kc = it - tap * G.kchunks;
                     if constexpr (XF) {
-                        // A tiles are written by the transform warps
-                    } else if (G.k1 > 0 && kc >= G.k1) {  // second source: fused 1x1 shortcut on the block input
+                        // The raw fp32 [rows][64] tile of this K-slice lands IN the stage's A region (rows * 256 B = the
+                        // bytes of the two fp16 planes it becomes); the transform warps rewrite it in place.  Raw tile
+                        // and weights share one barrier: the MMA only ever waits for the transform's arrival.
+                        mbar_expect_tx(xfull_bar(s), (uint32_t)((G.flat ? 128 : G.bw * G.bh) * 256 + 2 * BLOCK_N * 128));
+                        if (G.flat) tma_2d(sa, &tm_a_hi, xfull_bar(s), it * 64, (int)m0);
+                        else tma_4d(sa, &tm_a_hi, xfull_bar(s), it * 64, x0, y0, n_img);
+                        tma_3d(b_hi, &tm_w_hi, xfull_bar(s), kc * 64, tn * BLOCK_N, tap);
+                        tma_3d(b_lo, &tm_w_lo, xfull_bar(s), kc * 64, tn * BLOCK_N, tap);
+                        continue;
+                    }
+                    mbar_expect_tx(full_bar(s), tx_bytes);
+                    if (G.k1 > 0 && kc >= G.k1) {  // second source: fused 1x1 shortcut on the block input
                         const int c2 = (kc - G.k1) * 64;
                         if (G.flat) {
                             tma_2d(a_hi, &tm_a2_hi, full_bar(s), c2, (int)m0);
@@ -388,25 +393,24 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           }
         }
     } else if (XF && warp >= 2 + EP_WARPS) {
-        // ===================== A-operand transform (warps 10..17, XF only) =====================
-        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + 16*i: raw fp32 staging tile
-        // (row-major [128][64], filled by TMA) -> y = relu(x*scale+shift) -> fp16 hi/lo -> swizzled A tiles.
-        // All eight row loads of a K-slice are issued before the first value is used: the loop used to be one
-        // LDS -> 30-instruction dependent chain -> STS per row (ncu/SASS: no two loads in flight), which paced the
-        // tensor core at roughly half its rate on every pre-activation 1x1 layer.
+        // ===================== A-operand transform (warps 10.., XF only) =====================
+        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + (2*XF_WARPS)*i.  The raw fp32 tile
+        // (row-major [128][64], written by TMA into the stage's A region) becomes y = relu(x*scale+shift) -> fp16 hi/lo
+        // -> the two 128B-swizzled A planes, IN PLACE: every thread first pulls all of its rows into registers (all
+        // loads in flight together -- the loop used to be one LDS -> 30-instruction dependent chain -> STS per row and
+        // paced the tensor core at about half its rate), the transform warps meet at a named barrier, then write.
+        // No staging ring: the shared memory it occupied holds a third (fourth) operand stage, so TMA runs two
+        // K-slices ahead of the tensor core instead of one.
         const int t = threadIdx.x - (2 + EP_WARPS) * 32;
         const int l16 = t & 15, rg = t >> 4;
         const int wl = t & 31;
         constexpr int XR = 128 / (XF_WARPS * 2);  // rows per thread
         uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-        const uint8_t *raw_gen = smem_raw + (raw_base - smem_u32(smem_raw));
         int it_global = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int kc = 0; kc < kiters; ++kc, ++it_global) {  // taps == 1: kiters == kchunks
                 const int s = it_global % STAGES;
                 const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
-                const int r = it_global & 1;
-                const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
                 const int c = kc * 64 + l16 * 4;
                 // channels past cin: TMA zero-fills the raw tile there and scale = shift = 0 keeps them 0 (zero weights
                 // must not meet Inf/NaN)
@@ -415,20 +419,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     sc = *reinterpret_cast<const float4 *>(P.in_scale + c);
                     sh = *reinterpret_cast<const float4 *>(P.in_shift + c);
                 }
-                mbar_wait(rfull_bar(r), rph);
-                const uint8_t *src = raw_gen + r * RAW_TILE_BYTES + rg * 256 + l16 * 16;
+                uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
+                mbar_wait(xfull_bar(s), ph);
+                const uint8_t *src = a_hi + rg * 256 + l16 * 16;
                 float4 v[XR];
 #pragma unroll
                 for (int i = 0; i < XR; ++i) v[i] = *reinterpret_cast<const float4 *>(src + i * (XF_WARPS * 2) * 256);
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
+                asm volatile("bar.sync 1, %0;" ::"n"(XF_WARPS * 32) : "memory");  // every raw value is in a register
 #pragma unroll
                 for (int i = 0; i < XR; ++i) {
                     const int row = rg + (XF_WARPS * 2) * i;
                     float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
                                    fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
                     uint2 oh, ol;
-                    split4_f32<true>(y4, oh, ol);
+                    split4_f32<true>(y4, oh, ol, P.a.flag);
                     // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
                     const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
                     *reinterpret_cast<uint2 *>(a_hi + off) = oh;
@@ -436,7 +440,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (wl == 0) { mbar_arrive(full_bar(s)); mbar_arrive(rempty_bar(r)); }
+                if (wl == 0) mbar_arrive(full_bar(s));
             }
         }
     } else {
@@ -497,10 +501,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 }
             }
             // BN scale / shift of this lane's 4 channels per 32-channel block: requested before the accumulator wait
-            float4 esc[NCH], esh[NCH];
+            float4 esc[NCH], esh[NCH], ews[NCH];
 #pragma unroll
             for (int cc = 0; cc < NCH; ++cc) {
                 esc[cc] = make_float4(1.f, 1.f, 1.f, 1.f); esh[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ews[cc] = *reinterpret_cast<const float4 *>(P.w.oscale + tn * BLOCK_N + cb + cc * 32 + sub_g * 4);
                 if (MODE != EPI_UP2 && P.scale && P.out_split.hi) {
                     esc[cc] = *reinterpret_cast<const float4 *>(P.scale + tn * BLOCK_N + cb + cc * 32 + sub_g * 4);
                     esh[cc] = *reinterpret_cast<const float4 *>(P.shift + tn * BLOCK_N + cb + cc * 32 + sub_g * 4);
@@ -571,7 +576,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                         const float4 t = *reinterpret_cast<const float4 *>(&ep_tile[src * 32 + ((sub_g ^ (src & 7)) << 2)]);
                         if (pv[u]) {
                             float v[4] = {t.x, t.y, t.z, t.w};
-                            epi_finish<MODE>(P, pn[u], py[u], px[u], ch, v, pre[u], esc[c0 / 32], esh[c0 / 32]);
+                            epi_finish<MODE>(P, pn[u], py[u], px[u], ch, v, pre[u], esc[c0 / 32], esh[c0 / 32], ews[c0 / 32]);
                         }
                     }
                 }
@@ -775,7 +780,7 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
 template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false>
 static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 48 + EP_WARPS * 32 * 32 * 4 + 1024 +
-                         ((XF || RT) ? 1024 + 2 * 128 * 64 * 4 : 0);
+                         (RT ? 1024 + 2 * 128 * 64 * 4 : 0);
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr = false;
     if (!attr) {
@@ -832,9 +837,10 @@ static bool launch_halo(const ConvParams &P, const TcPlan &plan, TcGeom G, cudaS
 template <int BLOCK_N, int STAGES>
 static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     if (P.in_scale) {  // transformed input: only the shapes the plan produces (1x1, plain or upsample epilogue)
-        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {  // 2 operand stages: shared memory also holds the raw staging ring
-            if (P.up2) launch_tm<BLOCK_N, 2, EPI_UP2, true>(P, plan, G, s);
-            else launch_tm<BLOCK_N, 2, EPI_PLAIN, true>(P, plan, G, s);
+        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {  // raw tiles land in the operand stages themselves: 3 x 64 KB / 4 x 48 KB
+            constexpr int XS = BLOCK_N == 128 ? 3 : 4;
+            if (P.up2) launch_tm<BLOCK_N, XS, EPI_UP2, true>(P, plan, G, s);
+            else launch_tm<BLOCK_N, XS, EPI_PLAIN, true>(P, plan, G, s);
             return;
         }
         throw Error(-1, "conv_tc: transformed input with unsupported tile shape");

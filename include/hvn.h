@@ -32,7 +32,12 @@ typedef enum {
     HVN_ERR_CUDA = -2,        /* CUDA runtime or driver failure */
     HVN_ERR_WEIGHTS = -3,     /* missing / unexpected / mis-shaped checkpoint key (strict load) */
     HVN_ERR_CAPACITY = -4,    /* caller-provided table too small */
-    HVN_ERR_STATE = -5        /* call order (e.g. forward before weights are finalised) */
+    HVN_ERR_STATE = -5,       /* call order (e.g. forward before weights are finalised) */
+    HVN_ERR_RANGE = -6        /* an activation left the representable range of the engine's fp16 hi+lo storage
+                                 (|x| > 65504 * 2^act_shift); outputs of that call are invalid.  Raise option
+                                 "act_shift" (exact power-of-two rescaling of all activations) and run again.  Reported
+                                 by the call that synchronises: hvn_forward / hvn_forward_postproc / hvn_infer_tile,
+                                 or, after *_dev calls, hvn_sync / hvn_timer_stop. */
 } hvn_status;
 
 /* Instance-table row: one per instance id present in inst_map, ascending id.  int64 x 10.
@@ -67,6 +72,8 @@ int hvn_finalize_weights(hvn_ctx *ctx);
  *                      2 = auto + run every tcgen05 layer against the referee kernel and record the
  *                      per-layer max differences (hvn_debug_log);
  *                      "chunk" = patches per internal sub-batch (0 = auto);
+ *                      "act_shift" = s in 0..48: store activations as x * 2^-s (see HVN_ERR_RANGE; weights are
+ *                      re-derived, results are unchanged because powers of two are exact);
  *                      "profile" = 0 | 1 | 2 (see hvn_stage_ms);
  *                      tuning knobs (defaults are the measured best): "tc_halo" = 0 | 1 | 2 (k x k layers read
  *                      shifted windows of one halo tile: off / where its 8x16 tiling fits / every eligible layer),

@@ -87,3 +87,128 @@ def test_fused_forward_postproc_equals_two_step():
         inst, _ = process(pred[i], nr_types=6, return_centroids=True)
         assert np.array_equal(inst, finst[i])
     net.ctx.close()
+
+
+# ---- precision / range robustness: the fp16 hi+lo storage must not depend on the checkpoint's
+# ---- scales.  Referee for every case: the fp64 oracle forward on the SAME modified checkpoint.
+def _fp64_ref(x, sd, mode, nt):
+    from oracle import hovernet_torch as O
+    return O.infer_step(x, O.to_torch_state_dict(sd), mode, nt, dtype=torch.float64)
+
+
+def _check_against_fp64(sd, mode, nt, tag, rel_tol=1e-4, np_strict=True):
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    from hover_net_b200.models.hovernet.run_desc import infer_step
+    x = synth.make_patches(1, arch.PATCH_GEOMETRY[mode][0], seed=33)
+    ref = _fp64_ref(x, sd, mode, nt)
+    net = create_model(mode=mode, input_ch=3, nr_types=nt)
+    net.load_state_dict(sd, strict=True)
+    out = infer_step(x, net)
+    shift = net.ctx.counter("act_shift")
+    net.ctx.close()
+    assert np.isfinite(out).all(), tag
+    # NP probability: absolute; HV regression maps: relative to the map's own scale (1e-4 * max|ref|, floor 1e-4)
+    np_err = np.abs(out[..., -3] - ref[..., -3]).max()
+    hv_scale = max(1.0, float(np.abs(ref[..., -2:]).max()))
+    hv_err = np.abs(out[..., -2:] - ref[..., -2:]).max() / hv_scale
+    if not np_strict:  # saturated softmax over ~1e4 logits: a relative 1e-4 on the logits flips pixels at the 0/1 boundary
+        np_err = 0.0 if (np.abs(out[..., -3] - ref[..., -3]) > 1e-3).mean() < 0.01 else np_err
+    assert np_err <= 1e-4 and hv_err <= rel_tol, "%s: np err %.3e, hv rel err %.3e (scale %.3g, act_shift %d)" % (
+        tag, np_err, hv_err, hv_scale, shift)
+    return shift, hv_scale
+
+
+def test_layerwise_power_of_two_rescaling_does_not_change_the_result():
+    """Every convolution that feeds a BatchNorm has its weights multiplied by 2^+8 or 2^-8 and the BN's running mean /
+    variance rescaled to match: the network function is (up to eps) unchanged, but weights now span 2^-8 .. 2^+8 of
+    their original scale -- unscaled, the small ones would lose their `lo` plane to fp16 subnormals and the large ones
+    push pre-BN sums up by 256x.  The per-channel weight exponent makes the stored planes independent of it."""
+    mode, nt = "fast", 6
+    sd = dict(synth.make_state_dict(mode, nt, seed=0))
+    rng = np.random.default_rng(5)
+    n = 0
+    for k in list(sd):
+        if not k.endswith(".weight") or sd[k].ndim != 4:
+            continue
+        bn = k[: -len(".weight")] + "/bn"
+        if k == "conv0./.weight":
+            bn = "conv0.bn"
+        if bn + ".running_mean" not in sd:
+            continue
+        e = int(rng.choice([-8, 8]))
+        sd[k] = (sd[k] * np.float32(2.0 ** e)).astype(np.float32)
+        sd[bn + ".running_mean"] = (sd[bn + ".running_mean"] * np.float32(2.0 ** e)).astype(np.float32)
+        sd[bn + ".running_var"] = (sd[bn + ".running_var"] * np.float32(4.0 ** e)).astype(np.float32)
+        n += 1
+    assert n > 60
+    _check_against_fp64(sd, mode, nt, "2^+-8 per layer")
+
+
+def test_reference_weights_init_checkpoint():
+    """The reference's own initialisation (net_utils.py:18-32: Kaiming-normal fan_out convolutions, BN gamma 1 / beta 0,
+    fresh running statistics) drives the HV maps to ~1e4.  Intermediate activations leave fp16's
+    range: the engine must notice (HVN_ERR_RANGE), rescale by an exact power of two and still match the fp64 referee
+    to 1e-4 of the output scale -- never return a clamped map."""
+    mode, nt = "fast", 6
+    sd = dict(synth.make_state_dict(mode, nt, seed=0))
+    rng = np.random.default_rng(11)
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked") or k == "upsample2x.unpool_mat":
+            continue
+        if v.ndim == 4:
+            o, i, kh, kw = v.shape
+            sd[k] = (np.sqrt(2.0 / (o * kh * kw)) * rng.standard_normal(v.shape)).astype(np.float32)
+        elif k.endswith("running_mean") or k.endswith(".bias"):
+            sd[k] = np.zeros_like(v)
+        else:  # BN weight, running_var
+            sd[k] = np.ones_like(v)
+    shift, scale = _check_against_fp64(sd, mode, nt, "weights_init", rel_tol=2e-4, np_strict=False)
+    assert scale > 50.0, "expected large logits from the raw initialisation, got %.3g" % scale
+
+
+def test_heavy_tailed_weights():
+    """Student-t (3 d.o.f.) convolution weights: a few weights per channel are 10-50x the typical one."""
+    mode, nt = "original", None
+    sd = dict(synth.make_state_dict(mode, nt, seed=0))
+    rng = np.random.default_rng(13)
+    for k, v in sd.items():
+        if v.ndim == 4 and ".u0.conv." not in k:
+            t = rng.standard_t(3, v.shape).astype(np.float32)
+            sd[k] = (t * (np.std(v) / np.std(t))).astype(np.float32)
+    _check_against_fp64(sd, mode, nt, "student-t weights", rel_tol=2e-4)
+
+
+def test_range_overflow_is_an_error_not_a_clamp():
+    """Through the raw C ABI (no retry wrapper): activations pushed past 65504 return HVN_ERR_RANGE; with act_shift
+    raised the same call succeeds."""
+    import ctypes
+    from hover_net_b200 import _lib
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    mode, nt = "fast", 6
+    sd = dict(synth.make_state_dict(mode, nt, seed=0))
+    sd["conv0./.weight"] = (sd["conv0./.weight"] * np.float32(3.0e5)).astype(np.float32)
+    sd["conv0.bn.running_var"] = np.full_like(sd["conv0.bn.running_var"], 1.0)
+    net = create_model(mode=mode, input_ch=3, nr_types=nt)
+    net.load_state_dict(sd, strict=True)
+    x = synth.make_patches(1, 256, seed=3)
+    out = np.empty((1, 164, 164, 4), np.float32)
+    L = _lib.lib()
+    rc = L.hvn_forward(net.ctx._h, x.ctypes.data_as(ctypes.c_void_p), 1, 256, 256, out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == -6 and b"act_shift" in L.hvn_last_error()
+    net.ctx.set_option("act_shift", 12)
+    rc = L.hvn_forward(net.ctx._h, x.ctypes.data_as(ctypes.c_void_p), 1, 256, 256, out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0 and np.isfinite(out).all()
+    net.ctx.close()
+
+
+def test_act_shift_is_exact():
+    """Rescaling activations by 2^-6 changes nothing but the exponent fields: outputs agree to fp32 rounding of the
+    `lo` planes (not bit-for-bit: small values lose `lo` bits to fp16 subnormals)."""
+    from hover_net_b200.models.hovernet.run_desc import infer_step
+    net = _model("fast", 6, 0)
+    x = synth.make_patches(1, 256, seed=9)
+    a = infer_step(x, net)
+    net.ctx.set_option("act_shift", 6)
+    b = infer_step(x, net)
+    assert np.abs(a[..., 1:] - b[..., 1:]).max() <= 2e-5
+    net.ctx.close()
