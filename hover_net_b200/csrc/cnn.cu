@@ -211,6 +211,9 @@ void Model::make_conv_concat(const std::string &key, const std::string &name1, c
     cw.lo = dalloc<__half>(n, wallocs_, false);
     HVN_CUDA(cudaMemcpy(cw.hi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
     HVN_CUDA(cudaMemcpy(cw.lo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    float *d_osc = dalloc<float>(O, wallocs_, false);
+    HVN_CUDA(cudaMemcpy(d_osc, osc.data(), O * sizeof(float), cudaMemcpyHostToDevice));
+    cw.oscale = d_osc;
     conv_[key] = cw;
 }
 
