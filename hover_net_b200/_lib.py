@@ -66,6 +66,10 @@ class Context:
         self.device = int(device)
         self.mode = mode
         self.nr_types = nr_types
+        for kv in os.environ.get("HVN_OPTS", "").split(","):  # development knobs: HVN_OPTS="key=value,..."
+            if "=" in kv and mode is not None:
+                k, v = kv.split("=")
+                self.set_option(k.strip(), int(v))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -134,6 +134,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "flood_impl") postproc_set_flood_impl((int)value);
     else if (k == "fuse_up2") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->fuse_up2 = (int)value; }
     else if (k == "fuse_shortcut") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->fuse_shortcut = (int)value; }
+    else if (k == "stem_tc") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->stem_tc = (int)value; }
     else if (k == "xform") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->xform = (int)value; }
     else if (k == "branch_streams") { HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model"); c->model->branch_streams = (int)value; }
     else if (k == "tc_seg_chunks") tc_set_seg_chunks((int)value);

@@ -275,6 +275,35 @@ void Model::finalize() {
                             t[((ky * 7 + kx) * 3 + ch) * 64 + o] = w[((o * 3 + ch) * 7 + ky) * 7 + kx];
             conv0_w_ = dalloc<float>(t.size(), wallocs_, false);
             HVN_CUDA(cudaMemcpy(conv0_w_, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+            {   // tensor-core stem operand: [64 cout][192 k] split fp16, k = ky * 24 + kx * 3 + ch, zeros elsewhere
+                ConvWeights cw;
+                cw.taps = 1; cw.kh = cw.kw = 1; cw.cout = 64; cw.cin = 168; cw.cin_pad = 192;
+                std::vector<__half> hi((size_t)64 * 192, __float2half_rn(0.f)), lo(hi);
+                std::vector<float> osc(64, 1.f);
+                for (int o = 0; o < 64; ++o) {
+                    float mx = 0.f;
+                    for (int j = 0; j < 147; ++j) mx = std::max(mx, std::fabs(w[(size_t)o * 147 + j]));
+                    const int e = weight_exponent(mx);
+                    osc[o] = std::ldexp(1.f, -e);
+                    for (int ch = 0; ch < 3; ++ch)
+                        for (int ky = 0; ky < 7; ++ky)
+                            for (int kx = 0; kx < 7; ++kx) {
+                                const float v = std::ldexp(w[((o * 3 + ch) * 7 + ky) * 7 + kx], e);
+                                const __half h = __float2half_rn(v);
+                                const size_t d = (size_t)o * 192 + ky * 24 + kx * 3 + ch;
+                                hi[d] = h;
+                                lo[d] = __float2half_rn(v - __half2float(h));
+                            }
+                }
+                cw.hi = dalloc<__half>(hi.size(), wallocs_, false);
+                cw.lo = dalloc<__half>(lo.size(), wallocs_, false);
+                HVN_CUDA(cudaMemcpy(cw.hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                HVN_CUDA(cudaMemcpy(cw.lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                float *d_osc = dalloc<float>(64, wallocs_, false);
+                HVN_CUDA(cudaMemcpy(d_osc, osc.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+                cw.oscale = d_osc;
+                conv0_tc_w_ = cw;
+            }
         } else if (n.size() > 15 && n.compare(n.size() - 15, 15, ".u0.conv.weight") == 0) {
             std::vector<float> w = hostp(n);
             for (auto &x : w) x = std::ldexp(x, act_shift);  // the heads see features scaled by 2^-act_shift
@@ -693,8 +722,13 @@ void Model::forward(const uint8_t *imgs, int B, int H, int W, float *out, int ch
             }
             switch (op.kind) {
             case Op::CONV0:
-                launch_conv0(imgs + (size_t)b0 * H * W * 3, bc, H, W, op.c0_pad, conv0_w_, op.bn.scale, op.bn.shift,
-                             op.c0_out, s);
+                if (stem_tc && conv_path != 1 && conv0_tc_supported(H, W, op.c0_pad, op.c0_out)) {
+                    launch_conv0_tc(imgs + (size_t)b0 * H * W * 3, bc, H, W, op.c0_pad, conv0_tc_w_, op.bn.scale, op.bn.shift,
+                                    op.c0_out, s);
+                    ++tc_launches;
+                } else
+                    launch_conv0(imgs + (size_t)b0 * H * W * 3, bc, H, W, op.c0_pad, conv0_w_, op.bn.scale, op.bn.shift,
+                                 op.c0_out, s);
                 r.cls = "conv0";
                 break;
             case Op::CONV:

@@ -66,6 +66,7 @@ class Model {
     int tc_halo = 1;         // k x k stride-1 layers from one halo tile per channel block: 0 off, 1 where its 8 x 16 tiling fits, 2 all eligible
     int fuse_up2 = 0;        // 1: 2x upsample + skip add inside the conv epilogue; 0: separate streaming pass (faster)
     int fuse_shortcut = 1;   // fold each residual group's 1x1 shortcut into unit 0's conv3 (one GEMM over [a2 | x])
+    int stem_tc = 1;         // stem (conv0) on the tensor core (k_conv0_tc); 0: CUDA-core k_conv0
     int xform = 1;           // fuse pre-activation BN+ReLU into the consuming 1x1 conv's A-operand load
     int branch_streams = 1;  // run the decoder branches on separate streams
     int conv_path = 0;  // 0 auto (tcgen05 where eligible), 1 referee only, 2 auto + per-layer self test
@@ -99,6 +100,7 @@ class Model {
     std::map<std::string, ConvWeights> conv_;
     std::map<std::string, BNParams> bn_;
     float *conv0_w_ = nullptr;
+    ConvWeights conv0_tc_w_;  // the stem's weights as a [1][64][192] GEMM operand (k = ky * 24 + kx * 3 + ch)
     std::map<std::string, float *> head_w_, head_b_;
     std::vector<void *> wallocs_;
     std::map<std::string, std::unique_ptr<Plan>> plans_;

@@ -23,6 +23,10 @@ struct HeadParams {
 void launch_conv_ref(const ConvParams &P, cudaStream_t s);
 void launch_conv0(const uint8_t *img, int B, int H, int W, int pad, const float *wgt, const float *scale,
                   const float *shift, const SplitRef &out, cudaStream_t s);
+// tensor-core stem (conv_tc.cu): same result as launch_conv0 from weights in [1][64][192] split layout
+bool conv0_tc_supported(int H, int W, int pad, const SplitRef &out);
+void launch_conv0_tc(const uint8_t *img, int B, int H, int W, int pad, const ConvWeights &w, const float *scale,
+                     const float *shift, const SplitRef &out, cudaStream_t s);
 void launch_bnrelu(const RawRef &in, int B, const float *scale, const float *shift, const SplitRef &out,
                    cudaStream_t s);
 void launch_head(const HeadParams &P, cudaStream_t s);

@@ -598,6 +598,222 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem on the tensor core: conv0 7x7x3 -> 64 on the uint8 image (reference net_desc.py:27-35,103,115), BN+ReLU,
+// split store.  GEMM view: M = output pixels, N = 64, K = 7 rows x 24 (21 bytes of one image row = 7 taps x 3 channels,
+// padded to 24) = 168, padded to 192 = three 64-wide K-slices; the 8th "row" and the 3 pad bytes carry zero weights.
+// No operand of this GEMM exists in memory: eight producer warps gather it from a shared-memory strip of the input
+// rows -- 8 consecutive image bytes per 16-byte chunk of an A row -- through a 256-entry table that holds
+// (float)v / 255.0f (the reference's own `imgs / 255.0`, an IEEE division) already split into fp16 hi and lo, and write
+// the 128B-swizzled A tiles the MMA reads.  Weights (64 x 192 x {hi, lo} = 48 KB) stay resident in shared memory.
+// A tile = 128 consecutive output pixels of one image in raster order (at most two output rows, wo >= 128).
+constexpr int C0T_PROD_WARPS = 8, C0T_STAGES = 4, C0T_K = 192, C0T_ROWS = 8, C0T_STRIDE = 832;
+constexpr int C0T_THREADS = 64 + EP_WARPS * 32 + C0T_PROD_WARPS * 32;
+constexpr int C0T_SMEM = 1024 + C0T_STAGES * 2 * A_TILE_BYTES + 3 * 2 * 64 * 128 + 2 * C0T_ROWS * C0T_STRIDE + 8 * 256 * 4 + 256;
+
+__global__ void __launch_bounds__(C0T_THREADS, 1)
+k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+           const uint8_t *__restrict__ img, int B, int H, int W, int pad, const float *__restrict__ oscale,
+           const float *__restrict__ scale, const float *__restrict__ shift, const SplitRef out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr uint32_t STAGE = 2 * A_TILE_BYTES;                 // a_hi | a_lo of one 64-wide K-slice
+    constexpr uint32_t W_OFF = C0T_STAGES * STAGE;               // 3 x [w_hi 8 KB | w_lo 8 KB]
+    constexpr uint32_t STRIP_OFF = W_OFF + 3 * 2 * 64 * 128;     // 2 x [8 rows][832 B]
+    constexpr uint32_t LUT_OFF = STRIP_OFF + 2 * C0T_ROWS * C0T_STRIDE;  // [256 values][8 copies] of (hi | lo << 16)
+    constexpr uint32_t BAR_OFF = LUT_OFF + 8 * 256 * 4;
+    const uint32_t bar_base = smem_base + BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C0T_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C0T_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C0T_STAGES + 2 + s); };
+    const uint32_t wfull_bar = bar_base + 8u * (2 * C0T_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C0T_STAGES + 5);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + BAR_OFF + 8 * (2 * C0T_STAGES + 5));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ho = out.h, wo = out.w, hw = ho * wo;
+    const int tiles_img = (hw + 127) >> 7, total_tiles = B * tiles_img;
+    constexpr uint32_t TMEM_COLS = 256;  // 2 buffers x [hi*hi + lo*hi | hi*lo] of 64 columns
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < C0T_STAGES; ++s) { mbar_init(full_bar(s), C0T_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EP_WARPS * 32); }
+        mbar_init(wfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // (float)v / 255.0f as fp16 hi | lo, eight interleaved copies (lane & 7 picks one: fewer bank conflicts)
+        uint32_t *lut = reinterpret_cast<uint32_t *>(smem_gen + LUT_OFF);
+        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+            const float f = (float)(i >> 3) / 255.0f;
+            const __half h = __float2half_rn(f), l = __float2half_rn(f - __half2float(h));
+            lut[i] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {  // resident weights: three K-slices, hi and lo
+            mbar_expect_tx(wfull_bar, 3 * 2 * 64 * 128);
+            for (int s = 0; s < 3; ++s) {
+                tma_3d(smem_base + W_OFF + s * 16384, &tm_w_hi, wfull_bar, s * 64, 0, 0);
+                tma_3d(smem_base + W_OFF + s * 16384 + 8192, &tm_w_lo, wfull_bar, s * 64, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            mbar_wait(wfull_bar, 0);
+            int it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+                const int as = tc & 1;
+                mbar_wait(tempty_bar(as), ((uint32_t)(tc >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
+                for (int ks = 0; ks < 3; ++ks, ++it) {
+                    const int s = it % C0T_STAGES;
+                    mbar_wait(full_bar(s), (uint32_t)(it / C0T_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE;
+                    const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
+                                   db = umma_desc(smem_base + W_OFF + ks * 16384);  // [w_hi | w_lo]: 128 contiguous rows
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ko = (uint64_t)(2 * k);
+                        tc_mma_f16(d_tmem, da_hi + ko, db + ko, idesc2, (ks > 0 || k > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, da_lo + ko, db + ko, idesc, 1u);
+                    }
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(tfull_bar(as));
+            }
+        }
+    } else if (warp < 2 + EP_WARPS) {
+        // ===================== epilogue: TMEM -> BN+ReLU -> split store (64 B of hi and of lo per lane) =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2, cb = half * 32;
+        const int row = quad * 32 + lane;
+        int tc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+            const int n = tile / tiles_img, p = (tile - n * tiles_img) * 128 + row;
+            const int as = tc & 1;
+            mbar_wait(tfull_bar(as), (uint32_t)(tc >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 128 + cb);
+            uint32_t r0[32], r1[32];
+            tc_ld32(t_addr, r0);
+            tc_ld32(t_addr + 64u, r1);
+            tc_ld_wait();
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+            if (p < hw) {
+                const int oy = p / wo, ox = p - oy * wo;
+                const long long oo = n * out.sN + (long long)oy * out.sH + (long long)ox * out.sW + cb;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t[4];
+                    // per-channel constants straight from the read-only cache (96 registers per thread at 576 threads);
+                    // 2^-e folds into the BN scale exactly
+                    const float4 w4 = __ldg(reinterpret_cast<const float4 *>(oscale + cb + 4 * j));
+                    const float4 s4 = __ldg(reinterpret_cast<const float4 *>(scale + cb + 4 * j));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(shift + cb + 4 * j));
+                    const float m4[4] = {w4.x * s4.x, w4.y * s4.y, w4.z * s4.z, w4.w * s4.w}, c4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float v = __uint_as_float(r0[4 * j + i]) + __uint_as_float(r1[4 * j + i]);
+                        t[i] = fmaxf(v * m4[i] + c4[i], 0.f);
+                    }
+                    store_split4(out, oo + 4 * j, t);
+                }
+            }
+        }
+    } else {
+        // ===================== A-operand producers (warps 10..17) =====================
+        const int t = threadIdx.x - (2 + EP_WARPS) * 32;           // 0..255
+        const int j = t & 7;                                        // 16-byte chunk of the A row = group inside the K-slice
+        const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem_gen + LUT_OFF) + (lane & 7);
+        const int row_bytes = W * 3;
+        // input rows y0 - pad .. y0 - pad + 7 of image n, columns from -pad: zero outside the image.  26 bytes per
+        // thread: all loads are issued first (load_strip, early in a tile) and stored late (store_strip), so their
+        // global latency hides behind the A tiles built in between.
+        constexpr int SB = C0T_ROWS * C0T_STRIDE / (C0T_PROD_WARPS * 32);
+        static_assert(SB * C0T_PROD_WARPS * 32 == C0T_ROWS * C0T_STRIDE, "strip bytes must divide evenly");
+        uint8_t sreg[SB];
+        auto load_strip = [&](int tile) {
+            const int n = tile / tiles_img, p0 = (tile - n * tiles_img) * 128;
+            const int y0 = p0 / wo;
+            const uint8_t *im = img + (size_t)n * H * W * 3;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const int i = t + k * C0T_PROD_WARPS * 32;
+                const int r = i / C0T_STRIDE, cbyte = i - r * C0T_STRIDE;
+                const int iy = y0 - pad + r, ib = cbyte - pad * 3;
+                sreg[k] = (iy >= 0 && iy < H && ib >= 0 && ib < row_bytes) ? __ldg(im + (size_t)iy * row_bytes + ib) : (uint8_t)0;
+            }
+        };
+        auto store_strip = [&](int buf) {
+            uint8_t *strip = smem_gen + STRIP_OFF + buf * C0T_ROWS * C0T_STRIDE;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) strip[t + k * C0T_PROD_WARPS * 32] = sreg[k];
+        };
+        int it = 0, tcnt = 0;
+        if ((int)blockIdx.x < total_tiles) { load_strip(blockIdx.x); store_strip(0); }
+        asm volatile("bar.sync 2, %0;" ::"n"(C0T_PROD_WARPS * 32) : "memory");
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcnt) {
+            const int n = tile / tiles_img, p0 = (tile - n * tiles_img) * 128;
+            const int y0 = p0 / wo;
+            const uint8_t *strip = smem_gen + STRIP_OFF + (tcnt & 1) * C0T_ROWS * C0T_STRIDE;
+            const bool more = tile + (int)gridDim.x < total_tiles;
+            if (more) load_strip(tile + gridDim.x);   // next tile's rows: in flight while this tile is built
+            for (int ks = 0; ks < 3; ++ks, ++it) {
+                const int s = it % C0T_STAGES;
+                mbar_wait(empty_bar(s), ((uint32_t)(it / C0T_STAGES) & 1u) ^ 1u);
+                uint8_t *a_hi = smem_gen + s * STAGE, *a_lo = a_hi + A_TILE_BYTES;
+                const int G = ks * 8 + j, ky = G / 3, g = G - ky * 3;   // K = ky * 24 + g * 8 + i
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = (t >> 3) + 32 * q;                      // A row = pixel inside the tile
+                    uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+                    if (ky < 7) {
+                        int p = p0 + r;
+                        p = p < hw ? p : hw - 1;                          // rows past the image repeat its last pixel (never stored)
+                        const int y = p / wo, x = p - y * wo;
+                        const uint8_t *src = strip + (y - y0 + ky) * C0T_STRIDE + x * 3 + g * 8;
+                        uint32_t e[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) e[i] = lut[(uint32_t)src[i] * 8u];
+                        vh = make_uint4(__byte_perm(e[0], e[1], 0x5410), __byte_perm(e[2], e[3], 0x5410),
+                                        __byte_perm(e[4], e[5], 0x5410), __byte_perm(e[6], e[7], 0x5410));
+                        vl = make_uint4(__byte_perm(e[0], e[1], 0x7632), __byte_perm(e[2], e[3], 0x7632),
+                                        __byte_perm(e[4], e[5], 0x7632), __byte_perm(e[6], e[7], 0x7632));
+                    }
+                    const int off = r * 128 + ((j ^ (r & 7)) << 4);       // 128B swizzle: chunk j of row r at (j ^ (r & 7))
+                    *reinterpret_cast<uint4 *>(a_hi + off) = vh;
+                    *reinterpret_cast<uint4 *>(a_lo + off) = vl;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(s));
+            }
+            if (more) store_strip((tcnt + 1) & 1);   // the other buffer: last read one tile ago, before the barrier below
+            asm volatile("bar.sync 2, %0;" ::"n"(C0T_PROD_WARPS * 32) : "memory");  // next strip complete; this one free again
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -851,6 +1067,38 @@ static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, c
         launch_tm<BLOCK_N, STAGES, EPI_RES, false>(P, plan, G, s);
     }
     else launch_tm<BLOCK_N, STAGES, EPI_PLAIN, false>(P, plan, G, s);
+}
+
+// Stem launcher.  `w` = conv0 weights as [1 tap][64 cout][192 k] split fp16 (k = ky * 24 + kx * 3 + ch, zeros elsewhere).
+bool conv0_tc_supported(int H, int W, int pad, const SplitRef &out) {
+    return out.w >= 128 && out.c == 64 && (W + 2 * pad) * 3 + 3 <= C0T_STRIDE && out.h == H + 2 * pad - 6 && out.w == W + 2 * pad - 6 &&
+           !(reinterpret_cast<uintptr_t>(out.hi) & 15) && !(reinterpret_cast<uintptr_t>(out.lo) & 15) && out.sW % 8 == 0 &&
+           out.sH % 8 == 0 && out.sN % 8 == 0;
+}
+
+void launch_conv0_tc(const uint8_t *img, int B, int H, int W, int pad, const ConvWeights &w, const float *scale,
+                     const float *shift, const SplitRef &out, cudaStream_t s) {
+    HVN_CHECK(w.taps == 1 && w.cout == 64 && w.cin_pad == C0T_K, -1, "conv0_tc: unexpected weight layout");
+    static bool attr = false;
+    if (!attr) {
+        HVN_CUDA(cudaFuncSetAttribute(k_conv0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, C0T_SMEM));
+        attr = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    alignas(64) CUtensorMap w_hi, w_lo;
+    cuuint32_t ones[3] = {1, 1, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout, 1};
+    cuuint64_t str[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    HVN_CHECK(encode((unsigned char *)&w_hi, w.hi, 3, dims, str, box, ones) && encode((unsigned char *)&w_lo, w.lo, 3, dims, str, box, ones),
+              -2, "conv0_tc: tensor map encode failed");
+    const int tiles = B * cdiv((long long)out.h * out.w, 128);
+    k_conv0_tc<<<std::min(tiles, sms), C0T_THREADS, C0T_SMEM, s>>>(w_hi, w_lo, img, B, H, W, pad, w.oscale, scale, shift, out);
 }
 
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {

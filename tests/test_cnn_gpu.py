@@ -212,3 +212,20 @@ def test_act_shift_is_exact():
     b = infer_step(x, net)
     assert np.abs(a[..., 1:] - b[..., 1:]).max() <= 2e-5
     net.ctx.close()
+
+
+def test_tensor_core_stem_equals_cuda_core_stem():
+    """k_conv0_tc (stem as a GEMM whose A operand is gathered from the uint8 image through a /255 table) vs the
+    CUDA-core k_conv0: same network output to fp32 rounding, both modes (pad 3 / pad 0, 256 / 264 wide rows, a partial
+    last tile in `original` mode)."""
+    from hover_net_b200.models.hovernet.run_desc import infer_step
+    for mode, nt in (("fast", 6), ("original", None)):
+        net = _model(mode, nt, 0)
+        x = synth.make_patches(2, arch.PATCH_GEOMETRY[mode][0], seed=17)
+        x[0, :8] = 255; x[1, -5:, -7:] = 0       # saturated / zero borders exercise the padding columns
+        net.ctx.set_option("stem_tc", 1)
+        a = infer_step(x, net)
+        net.ctx.set_option("stem_tc", 0)
+        b = infer_step(x, net)
+        assert np.isfinite(a).all() and np.abs(a[..., -3:] - b[..., -3:]).max() <= 2e-5, mode
+        net.ctx.close()

@@ -1,7 +1,8 @@
 #!/bin/bash
 # round-2 GPU session 3: XF in-place transform (3/4 stages), per-channel weight exponents, range guard: tests + layers + bench
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2b_tests.log 2>&1; echo "tests rc=$?"; tail -25 gpurun_out/r2b_tests.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2b_tests.log 2>&1; rc=$?; echo "tests rc=$rc"; tail -25 gpurun_out/r2b_tests.log
+if [ $rc -ne 0 ]; then HVN_OPTS=stem_tc=0 timeout 600 python -m pytest tests/test_cnn_gpu.py -m gpu -q > gpurun_out/r2b_tests_nostem.log 2>&1; echo "no-stem rc=$?"; tail -8 gpurun_out/r2b_tests_nostem.log; fi
 timeout 300 python tools/gpu_diag.py layers original 16 > gpurun_out/r2b_layers_orig16.log 2>&1
 timeout 300 python tools/gpu_diag.py layers fast 32 > gpurun_out/r2b_layers_fast32.log 2>&1
 tail -7 gpurun_out/r2b_layers_orig16.log; tail -7 gpurun_out/r2b_layers_fast32.log

@@ -1,12 +1,23 @@
-"""Small end-to-end run for compute-sanitizer (memcheck): 1 fast-mode patch through CNN + post-processing
-(tcgen05 path incl. the HALO variant and the stem), device contours, the whole-image tile path on a small image,
-and a 300x200 synthetic map through the generic (large-map) flood.  HVN_SAN_REFEREE=1 adds the CUDA-core referee."""
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): 1 patch through CNN +
+post-processing (every k_conv_tc variant the plan uses -- plain, XF in-place transform, RT, two-source, HALO on every
+eligible layer -- and the tensor-core stem), device contours, the whole-image tile path on a small image, the packed
+table gather kernel, and a 300x200 synthetic map through the generic (large-map) flood.
+HVN_SAN_MODE=original runs the 270x270 / 5x5 variant of the CNN part only; HVN_SAN_REFEREE=1 adds the CUDA-core referee."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from hover_net_b200 import synth
 from hover_net_b200.models.hovernet.net_desc import create_model
 
+if os.environ.get("HVN_SAN_MODE") == "original":
+    net = create_model(mode="original", nr_types=5)
+    net.load_state_dict(synth.make_state_dict("original", 5, 0))
+    net.ctx.set_option("tc_halo", 2)
+    x = synth.make_patches(1, 270, seed=1)
+    pred, inst, tab, n = net.ctx.forward_postproc(x)
+    print("tc path (original) ok", int(n[0]), bool(np.isfinite(pred).all()))
+    net.ctx.close()
+    sys.exit(0)
 net = create_model(mode="fast", nr_types=6)
 net.load_state_dict(synth.make_state_dict("fast", 6, 0))
 net.ctx.set_option("tc_halo", 2)
