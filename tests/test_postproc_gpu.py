@@ -165,3 +165,31 @@ def test_process_contours_match_oracle_process(oracle_pp):
             assert np.array_equal(info[k]["centroid"], oinfo[k]["centroid"])
             assert np.array_equal(info[k]["bbox"], oinfo[k]["bbox"])
             assert info[k]["type"] == oinfo[k]["type"] and info[k]["type_prob"] == oinfo[k]["type_prob"]
+
+
+def test_pack_tables_kernel_matches_padded_tables():
+    """hvn_pack_tables_dev (the send buffer of the end-of-batch gather): packed rows == the padded tables' valid rows in
+    map order, offs == exclusive prefix of n_rows; a too-small capacity drops rows but keeps offs exact."""
+    import torch
+    from hover_net_b200 import _lib
+    from hover_net_b200.dist import PackedGather
+    nt, n = 6, 5
+    maps = np.stack([synth.synth_pred_map(96, 112, nt, 40 + s) for s in range(n)])
+    maps[3, ..., 1] = 0.0                                    # a map without instances
+    c = _lib.Context(0)
+    inst, table, nrows = c.postproc(maps, nt)
+    max_rows = table.shape[1]
+    d_tab = torch.from_numpy(table).cuda()
+    d_nr = torch.from_numpy(nrows).cuda()
+    pg = PackedGather(c, n, max_rows, int(nrows.sum()) + 3, 1, torch.device("cuda", 0))
+    k = pg.launch(d_tab, d_nr)
+    c.sync()
+    (offs, packed), = pg.rows(k)
+    assert np.array_equal(offs, np.concatenate([[0], np.cumsum(nrows)]))
+    assert np.array_equal(packed, np.concatenate([table[i, : nrows[i]] for i in range(n)]))
+    small = PackedGather(c, n, max_rows, int(nrows[0]) + 1, 1, torch.device("cuda", 0))
+    k = small.launch(d_tab, d_nr)
+    c.sync()
+    (offs2, packed2), = small.rows(k)
+    assert np.array_equal(offs2, offs) and np.array_equal(packed2, packed[: int(nrows[0]) + 1])
+    c.close()

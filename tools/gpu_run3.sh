@@ -16,3 +16,4 @@ for f in sorted(glob.glob('gpurun_out/r2b_bench_*.log')):
         print(f, 'value %.1f e2e %.1f ms/step %.1f frac %.3f cnn %.1f pp %.2f' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['kernel_classes']['cnn_total_ms'], d['kernel_classes']['postproc']['ms']))
     except Exception as e: print(f, 'ERR', e); print(open(f).read()[-1500:])
 PY
+timeout 120 ./tools/tma_bw_probe > gpurun_out/r2_tma_bw_probe.log 2>&1; cat gpurun_out/r2_tma_bw_probe.log
