@@ -622,16 +622,21 @@ def run_wsi(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     mode, nt = args.mode, args.nr_types
-    work = tempfile.mkdtemp(prefix="hvn_wsi_%d_" % rank)
-    os.makedirs(work + "/in"); os.makedirs(work + "/msk"); os.makedirs(work + "/out")
-    np.save(work + "/in/slide.npy", synth_image(args.size))
-    cv2.imwrite(work + "/msk/slide.png", np.full((max(8, args.size // 32),) * 2, 255, np.uint8))
+    # one slide file for all ranks (a 40000^2 slide is 4.8 GB): rank 0 writes it, the others wait at the barrier
+    work = os.path.join(tempfile.gettempdir(), "hvn_wsi_bench_%s" % os.environ.get("MASTER_PORT", "0"))
+    if rank == 0:
+        shutil.rmtree(work, ignore_errors=True)
+        os.makedirs(work + "/in"); os.makedirs(work + "/msk"); os.makedirs(work + "/out")
+        np.save(work + "/in/slide.npy", synth_image(args.size))
+        cv2.imwrite(work + "/msk/slide.png", np.full((max(8, args.size // 32),) * 2, 255, np.uint8))
+    if world > 1:
+        dist.barrier()
     win, out = (256, 164) if mode == "fast" else (270, 80)
     mgr = InferManager(method={"model_args": {"nr_types": nt, "mode": mode, "device": local},
                                "model_path": synth.make_state_dict(mode, nt, seed=0)}, type_info_path=None)
     run_args = {"batch_size": args.batch, "nr_inference_workers": 0, "nr_post_proc_workers": 0, "patch_input_shape": win,
                 "patch_output_shape": out, "input_dir": work + "/in", "output_dir": work + "/out", "input_mask_dir": work + "/msk",
-                "proc_mag": 40, "cache_path": work + "/cache", "chunk_shape": 10000, "tile_shape": 2048, "ambiguous_size": 128,
+                "proc_mag": 40, "cache_path": work + "/cache%d" % rank, "chunk_shape": 10000, "tile_shape": 2048, "ambiguous_size": 128,
                 "save_thumb": False, "save_mask": False}
     if world > 1:
         dist.barrier()
@@ -664,7 +669,8 @@ def run_wsi(args):
         dist.barrier()
         dist.destroy_process_group()
     mgr.net.ctx.close()
-    shutil.rmtree(work, ignore_errors=True)
+    if rank == 0:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def main():

@@ -157,9 +157,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     // XF only: raw_full[2], raw_empty[2] barriers and a 2-slot ring of raw fp32 [128][64] staging tiles
     auto rfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * r; };
     auto rempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * (2 + r); };
-    // XF: one "raw tile + weights landed" barrier per stage (same four slots; STAGES <= 4)
-    auto xfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * s; };
-    static_assert(!XF || STAGES <= 4, "XF: at most four stages (barrier slots)");
     const uint32_t ep_base = bar_base + 8u * (2 * STAGES + 4) + 48u;  // 8 warps x [32][32] fp32 transpose tiles (XOR-swizzled)
     const uint32_t raw_base = (ep_base + EP_WARPS * 4096u + 1023u) & ~1023u;
     constexpr uint32_t RAW_TILE_BYTES = 128 * 64 * 4;
@@ -171,10 +168,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     constexpr uint32_t TMEM_COLS = 4 * BLOCK_N;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), XF ? 1 + XF_WARPS : 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), BLOCK_N >= 64 ? 256 : 128); }
-        if (XF) for (int s = 0; s < STAGES; ++s) mbar_init(xfull_bar(s), 1);
-        if (RT) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), EP_WARPS); }
+        if (XF || RT) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), XF ? XF_WARPS : EP_WARPS); }
         if (HALO) for (int r = 0; r < 2; ++r) { mbar_init(rfull_bar(r), 1); mbar_init(rempty_bar(r), 1); }  // halo slots: full / empty
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -269,14 +265,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                                    b_lo = b_hi + BLOCK_N * 128;
                     const int tap = it / G.kchunks, kc = it - tap * G.kchunks;
                     if constexpr (XF) {
-                        // The raw fp32 [rows][64] tile of this K-slice lands IN the stage's A region (rows * 256 B = the
-                        // bytes of the two fp16 planes it becomes); the transform warps rewrite it in place.  Raw tile
-                        // and weights share one barrier: the MMA only ever waits for the transform's arrival.
-                        mbar_expect_tx(xfull_bar(s), (uint32_t)((G.flat ? 128 : G.bw * G.bh) * 256 + 2 * BLOCK_N * 128));
-                        if (G.flat) tma_2d(sa, &tm_a_hi, xfull_bar(s), it * 64, (int)m0);
-                        else tma_4d(sa, &tm_a_hi, xfull_bar(s), it * 64, x0, y0, n_img);
-                        tma_3d(b_hi, &tm_w_hi, xfull_bar(s), kc * 64, tn * BLOCK_N, tap);
-                        tma_3d(b_lo, &tm_w_lo, xfull_bar(s), kc * 64, tn * BLOCK_N, tap);
+                        // raw fp32 A tile of this K-slice -> staging ring (tm_a_hi is the fp32 map); the A planes of the
+                        // stage are written by the transform warps, the weights land beside them
+                        const int r = it_global & 1;
+                        const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
+                        mbar_wait(rempty_bar(r), rph ^ 1u);
+                        mbar_expect_tx(rfull_bar(r), (uint32_t)((G.flat ? 128 : G.bw * G.bh) * 256));
+                        if (G.flat) tma_2d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), it * 64, (int)m0);
+                        else tma_4d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), it * 64, x0, y0, n_img);
+                        mbar_expect_tx(full_bar(s), (uint32_t)(2 * BLOCK_N * 128));
+                        tma_3d(b_hi, &tm_w_hi, full_bar(s), kc * 64, tn * BLOCK_N, tap);
+                        tma_3d(b_lo, &tm_w_lo, full_bar(s), kc * 64, tn * BLOCK_N, tap);
                         continue;
                     }
                     mbar_expect_tx(full_bar(s), tx_bytes);
@@ -393,24 +392,26 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           }
         }
     } else if (XF && warp >= 2 + EP_WARPS) {
-        // ===================== A-operand transform (warps 10.., XF only) =====================
-        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + (2*XF_WARPS)*i.  The raw fp32 tile
-        // (row-major [128][64], written by TMA into the stage's A region) becomes y = relu(x*scale+shift) -> fp16 hi/lo
-        // -> the two 128B-swizzled A planes, IN PLACE: every thread first pulls all of its rows into registers (all
-        // loads in flight together -- the loop used to be one LDS -> 30-instruction dependent chain -> STS per row and
-        // paced the tensor core at about half its rate), the transform warps meet at a named barrier, then write.
-        // No staging ring: the shared memory it occupied holds a third (fourth) operand stage, so TMA runs two
-        // K-slices ahead of the tensor core instead of one.
+        // ===================== A-operand transform (warps 10..17, XF only) =====================
+        // thread -> (row group rg = t>>4, float4 column l16 = t&15), rows rg + 16*i: raw fp32 staging tile
+        // (row-major [128][64], filled by TMA) -> y = relu(x*scale+shift) -> fp16 hi/lo -> swizzled A tiles.
+        // All eight row loads of a K-slice are issued before the first value is used: the loop used to be one
+        // LDS -> 30-instruction dependent chain -> STS per row (ncu/SASS: no two loads in flight), which paced the
+        // tensor core at roughly half its rate on every pre-activation 1x1 layer.
         const int t = threadIdx.x - (2 + EP_WARPS) * 32;
         const int l16 = t & 15, rg = t >> 4;
         const int wl = t & 31;
         constexpr int XR = 128 / (XF_WARPS * 2);  // rows per thread
         uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+        const uint8_t *raw_gen = smem_raw + (raw_base - smem_u32(smem_raw));
+        const int vrows = G.flat ? 128 : G.bw * G.bh;
         int it_global = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int kc = 0; kc < kiters; ++kc, ++it_global) {  // taps == 1: kiters == kchunks
                 const int s = it_global % STAGES;
                 const uint32_t ph = (uint32_t)(it_global / STAGES) & 1u;
+                const int r = it_global & 1;
+                const uint32_t rph = (uint32_t)(it_global >> 1) & 1u;
                 const int c = kc * 64 + l16 * 4;
                 // channels past cin: TMA zero-fills the raw tile there and scale = shift = 0 keeps them 0 (zero weights
                 // must not meet Inf/NaN)
@@ -419,20 +420,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     sc = *reinterpret_cast<const float4 *>(P.in_scale + c);
                     sh = *reinterpret_cast<const float4 *>(P.in_shift + c);
                 }
-                uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
-                mbar_wait(xfull_bar(s), ph);
-                const uint8_t *src = a_hi + rg * 256 + l16 * 16;
+                mbar_wait(rfull_bar(r), rph);
+                const uint8_t *src = raw_gen + r * RAW_TILE_BYTES + rg * 256 + l16 * 16;
                 float4 v[XR];
 #pragma unroll
                 for (int i = 0; i < XR; ++i) v[i] = *reinterpret_cast<const float4 *>(src + i * (XF_WARPS * 2) * 256);
-                asm volatile("bar.sync 1, %0;" ::"n"(XF_WARPS * 32) : "memory");  // every raw value is in a register
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                 for (int i = 0; i < XR; ++i) {
                     const int row = rg + (XF_WARPS * 2) * i;
                     float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
                                    fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
                     uint2 oh, ol;
-                    split4_f32<true>(y4, oh, ol, P.a.flag);
+                    // range guard only on rows TMA wrote: rows past a partial box keep stale (arbitrary) bits
+                    split4_f32<true>(y4, oh, ol, row < vrows ? P.a.flag : nullptr);
                     // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
                     const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
                     *reinterpret_cast<uint2 *>(a_hi + off) = oh;
@@ -440,7 +442,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (wl == 0) mbar_arrive(full_bar(s));
+                if (wl == 0) { mbar_arrive(full_bar(s)); mbar_arrive(rempty_bar(r)); }
             }
         }
     } else {
@@ -601,14 +603,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 // Stem on the tensor core: conv0 7x7x3 -> 64 on the uint8 image (reference net_desc.py:27-35,103,115), BN+ReLU,
 // split store.  GEMM view: M = output pixels, N = 64, K = 7 rows x 24 (21 bytes of one image row = 7 taps x 3 channels,
 // padded to 24) = 168, padded to 192 = three 64-wide K-slices; the 8th "row" and the 3 pad bytes carry zero weights.
-// No operand of this GEMM exists in memory: eight producer warps gather it from a shared-memory strip of the input
-// rows -- 8 consecutive image bytes per 16-byte chunk of an A row -- through a 256-entry table that holds
-// (float)v / 255.0f (the reference's own `imgs / 255.0`, an IEEE division) already split into fp16 hi and lo, and write
-// the 128B-swizzled A tiles the MMA reads.  Weights (64 x 192 x {hi, lo} = 48 KB) stay resident in shared memory.
+// No operand of this GEMM exists in memory.  Per tile the eight producer warps fetch the 8 input rows it touches, push
+// every byte ONCE through a 256-entry table holding (float)v / 255.0f (the reference's own `imgs / 255.0`, an IEEE
+// division) already split into fp16 hi | lo, and keep the converted strip in shared memory; an A row's 16-byte chunk is
+// then 8 consecutive words of that strip (hi halves to one plane, lo halves to the other), written 128B-swizzled where
+// the MMA reads it.  (A first version looked every A element up separately from a byte strip: 49 lookups per input
+// byte, 15 k cycles per tile in shared-memory wavefronts -- 8x the tensor core's time.)  Weights (64 x 192 x {hi, lo} =
+// 48 KB) stay resident in shared memory.
 // A tile = 128 consecutive output pixels of one image in raster order (at most two output rows, wo >= 128).
-constexpr int C0T_PROD_WARPS = 8, C0T_STAGES = 4, C0T_K = 192, C0T_ROWS = 8, C0T_STRIDE = 832;
+constexpr int C0T_PROD_WARPS = 8, C0T_STAGES = 3, C0T_K = 192, C0T_ROWS = 8, C0T_STRIDE = 832;
+constexpr int C0T_PSTRIDE = 833;  // words per row of the converted strip: odd, so the 7 filter rows fall into different banks
 constexpr int C0T_THREADS = 64 + EP_WARPS * 32 + C0T_PROD_WARPS * 32;
-constexpr int C0T_SMEM = 1024 + C0T_STAGES * 2 * A_TILE_BYTES + 3 * 2 * 64 * 128 + 2 * C0T_ROWS * C0T_STRIDE + 8 * 256 * 4 + 256;
+constexpr int C0T_SMEM = 1024 + C0T_STAGES * 2 * A_TILE_BYTES + 3 * 2 * 64 * 128 + 2 * C0T_ROWS * C0T_PSTRIDE * 4 + 256 * 4 + 256;
 
 __global__ void __launch_bounds__(C0T_THREADS, 1)
 k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -619,9 +625,9 @@ k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ 
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     constexpr uint32_t STAGE = 2 * A_TILE_BYTES;                 // a_hi | a_lo of one 64-wide K-slice
     constexpr uint32_t W_OFF = C0T_STAGES * STAGE;               // 3 x [w_hi 8 KB | w_lo 8 KB]
-    constexpr uint32_t STRIP_OFF = W_OFF + 3 * 2 * 64 * 128;     // 2 x [8 rows][832 B]
-    constexpr uint32_t LUT_OFF = STRIP_OFF + 2 * C0T_ROWS * C0T_STRIDE;  // [256 values][8 copies] of (hi | lo << 16)
-    constexpr uint32_t BAR_OFF = LUT_OFF + 8 * 256 * 4;
+    constexpr uint32_t STRIP_OFF = W_OFF + 3 * 2 * 64 * 128;     // 2 x [8 rows][833 words] converted strip (hi | lo << 16)
+    constexpr uint32_t LUT_OFF = STRIP_OFF + 2 * C0T_ROWS * C0T_PSTRIDE * 4;  // [256] (hi | lo << 16) of v / 255
+    constexpr uint32_t BAR_OFF = LUT_OFF + 256 * 4;
     const uint32_t bar_base = smem_base + BAR_OFF;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C0T_STAGES + s); };
@@ -645,10 +651,10 @@ k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {   // (float)v / 255.0f as fp16 hi | lo, eight interleaved copies (lane & 7 picks one: fewer bank conflicts)
+    {   // (float)v / 255.0f as fp16 hi | lo
         uint32_t *lut = reinterpret_cast<uint32_t *>(smem_gen + LUT_OFF);
-        for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-            const float f = (float)(i >> 3) / 255.0f;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            const float f = (float)i / 255.0f;
             const __half h = __float2half_rn(f), l = __float2half_rn(f - __half2float(h));
             lut[i] = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
         }
@@ -737,7 +743,7 @@ k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ 
         // ===================== A-operand producers (warps 10..17) =====================
         const int t = threadIdx.x - (2 + EP_WARPS) * 32;           // 0..255
         const int j = t & 7;                                        // 16-byte chunk of the A row = group inside the K-slice
-        const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem_gen + LUT_OFF) + (lane & 7);
+        const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem_gen + LUT_OFF);
         const int row_bytes = W * 3;
         // input rows y0 - pad .. y0 - pad + 7 of image n, columns from -pad: zero outside the image.  26 bytes per
         // thread: all loads are issued first (load_strip, early in a tile) and stored late (store_strip), so their
@@ -757,10 +763,14 @@ k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ 
                 sreg[k] = (iy >= 0 && iy < H && ib >= 0 && ib < row_bytes) ? __ldg(im + (size_t)iy * row_bytes + ib) : (uint8_t)0;
             }
         };
-        auto store_strip = [&](int buf) {
-            uint8_t *strip = smem_gen + STRIP_OFF + buf * C0T_ROWS * C0T_STRIDE;
+        auto store_strip = [&](int buf) {  // convert once per input byte
+            uint32_t *strip = reinterpret_cast<uint32_t *>(smem_gen + STRIP_OFF) + buf * C0T_ROWS * C0T_PSTRIDE;
 #pragma unroll
-            for (int k = 0; k < SB; ++k) strip[t + k * C0T_PROD_WARPS * 32] = sreg[k];
+            for (int k = 0; k < SB; ++k) {
+                const int i = t + k * C0T_PROD_WARPS * 32;
+                const int r = i / C0T_STRIDE, cbyte = i - r * C0T_STRIDE;
+                strip[r * C0T_PSTRIDE + cbyte] = lut[sreg[k]];
+            }
         };
         int it = 0, tcnt = 0;
         if ((int)blockIdx.x < total_tiles) { load_strip(blockIdx.x); store_strip(0); }
@@ -768,7 +778,7 @@ k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcnt) {
             const int n = tile / tiles_img, p0 = (tile - n * tiles_img) * 128;
             const int y0 = p0 / wo;
-            const uint8_t *strip = smem_gen + STRIP_OFF + (tcnt & 1) * C0T_ROWS * C0T_STRIDE;
+            const uint32_t *strip = reinterpret_cast<const uint32_t *>(smem_gen + STRIP_OFF) + (tcnt & 1) * C0T_ROWS * C0T_PSTRIDE;
             const bool more = tile + (int)gridDim.x < total_tiles;
             if (more) load_strip(tile + gridDim.x);   // next tile's rows: in flight while this tile is built
             for (int ks = 0; ks < 3; ++ks, ++it) {
@@ -784,10 +794,10 @@ k_conv0_tc(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ 
                         int p = p0 + r;
                         p = p < hw ? p : hw - 1;                          // rows past the image repeat its last pixel (never stored)
                         const int y = p / wo, x = p - y * wo;
-                        const uint8_t *src = strip + (y - y0 + ky) * C0T_STRIDE + x * 3 + g * 8;
+                        const uint32_t *src = strip + (y - y0 + ky) * C0T_PSTRIDE + x * 3 + g * 8;
                         uint32_t e[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) e[i] = lut[(uint32_t)src[i] * 8u];
+                        for (int i = 0; i < 8; ++i) e[i] = src[i];
                         vh = make_uint4(__byte_perm(e[0], e[1], 0x5410), __byte_perm(e[2], e[3], 0x5410),
                                         __byte_perm(e[4], e[5], 0x5410), __byte_perm(e[6], e[7], 0x5410));
                         vl = make_uint4(__byte_perm(e[0], e[1], 0x7632), __byte_perm(e[2], e[3], 0x7632),
@@ -996,7 +1006,7 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
 template <int BLOCK_N, int STAGES, int MODE, bool XF, bool RT = false>
 static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     constexpr int smem = STAGES * tc_stage_bytes<BLOCK_N>() + 8 * (2 * STAGES + 4) + 48 + EP_WARPS * 32 * 32 * 4 + 1024 +
-                         (RT ? 1024 + 2 * 128 * 64 * 4 : 0);
+                         ((XF || RT) ? 1024 + 2 * 128 * 64 * 4 : 0);
     static_assert(smem <= 232448, "shared memory budget exceeded");
     static bool attr = false;
     if (!attr) {
@@ -1053,8 +1063,12 @@ static bool launch_halo(const ConvParams &P, const TcPlan &plan, TcGeom G, cudaS
 template <int BLOCK_N, int STAGES>
 static void launch_t(const ConvParams &P, const TcPlan &plan, const TcGeom &G, cudaStream_t s) {
     if (P.in_scale) {  // transformed input: only the shapes the plan produces (1x1, plain or upsample epilogue)
-        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {  // raw tiles land in the operand stages themselves: 3 x 64 KB / 4 x 48 KB
-            constexpr int XS = BLOCK_N == 128 ? 3 : 4;
+        if constexpr (BLOCK_N == 128 || BLOCK_N == 64) {
+            // 2 operand stages: shared memory also holds the raw staging ring.  An in-place
+            // variant (raw tile landing in the stage's A region, 3 / 4 stages, no ring) was measured SLOWER on B200
+            // (d2 conv1 251 -> 207 TFLOP/s, gpurun_out/r2b_layers_orig16.log): all loads of a slice had to complete and
+            // meet at a barrier before the first store, which cost more than the extra stage of TMA look-ahead gave.
+            constexpr int XS = 2;
             if (P.up2) launch_tm<BLOCK_N, XS, EPI_UP2, true>(P, plan, G, s);
             else launch_tm<BLOCK_N, XS, EPI_PLAIN, true>(P, plan, G, s);
             return;

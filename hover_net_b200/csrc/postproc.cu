@@ -870,7 +870,6 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
     const float scale = kmax > kmin ? (float)NB / (kmax - kmin) : 0.f;
     int nb = st[m].nblobs;
     if (nb > max_blobs) nb = max_blobs;
-    const int pass = warp < 2 ? 0 : 1;
     u64 summary = 0ull;  // bit j <=> bitmap[j] != 0   (NB/32 <= 64 words)
 
     auto bucket_of = [&](float k) {
@@ -911,6 +910,9 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
         return (int)p;
     };
 
+    // warps 0-1 take the large blobs first (their queues have 2048 buckets), then join the others on the small ones:
+    // on nuclei-like maps every blob is small and two of the eight flood lanes used to sit idle
+    for (int pass = warp < 2 ? 0 : 1; pass < 2; ++pass)
     while (true) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&s_next[pass], 1);
