@@ -69,8 +69,8 @@ def main(tag):
     if os.path.exists(lp):
         tot, cnt = launches(lp)
         T = sum(tot.values())
-        out += ["## Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 "
-                "--warmup 1 --batch 32 --no-cpu-baseline`", "",
+        out += ["## Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none " +
+                os.environ.get("NCU_LAUNCH_CMD", "python bench.py --steps 1 --warmup 1 --batch 32 --no-cpu-baseline") + "`", "",
                 "Per-launch times under ncu are serialised and cold-cache: read the SHARES. Total %.1f ms over %d launches "
                 "(warm-up step + timed step + e2e step + profile passes)." % (T, sum(cnt.values())), "",
                 "| kernel | launches | total ms | share |", "|---|---:|---:|---:|"]
@@ -90,10 +90,11 @@ def main(tag):
     if os.path.exists(tp):
         import json
         tr = traffic(tp)
+        mode, batch = os.environ.get("NCU_MODE", "fast"), int(os.environ.get("NCU_BATCH", "32"))
         meta = {"command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
-                           "python tools/ncu_target.py 32", "batch": 32, "kernels": tr}
+                           "python tools/ncu_target.py %d %s" % (batch, mode), "batch": batch, "mode": mode, "kernels": tr}
         json.dump(meta, open(os.path.join(ROOT, "profiles", "%s_traffic.json" % tag), "w"), indent=1)
-        out += ["## DRAM traffic per kernel, one forward+post-proc pass at B=32 (chunk 32)", "",
+        out += ["## DRAM traffic per kernel, one forward+post-proc pass at B=%d (%s mode, one chunk)" % (batch, mode), "",
                 "| kernel | launches | DRAM bytes (read+write) | per launch |", "|---|---:|---:|---:|"]
         for k, v in sorted(tr.items(), key=lambda x: -x[1]["dram_bytes"])[:12]:
             out.append("| `%s` | %d | %.3f GB | %.1f MB |" % (k, v["launches"], v["dram_bytes"] / 1e9,
