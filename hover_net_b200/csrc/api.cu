@@ -271,6 +271,7 @@ int hvn_postproc(hvn_ctx *c, const float *pred, int n, int H, int W, int C, int 
     float *d_pred = c->io_arena.take<float>(px * C);
     int32_t *d_inst = c->io_arena.take<int32_t>(px);
     int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    HVN_CUDA(cudaMemsetAsync(d_tab, 0, tb * 8, c->stream));  // rows past n_rows go back to the caller as zeros
     int32_t *d_nr = c->io_arena.take<int32_t>(n);
     HVN_CUDA(cudaMemcpyAsync(d_pred, pred, px * C * 4, cudaMemcpyHostToDevice, c->stream));
     run_postproc(c, d_pred, n, H, W, C, nr_types, d_inst, d_tab, max_rows, d_nr);
@@ -309,6 +310,7 @@ int hvn_postproc_contours(hvn_ctx *c, const float *pred, int n, int H, int W, in
     float *d_pred = c->io_arena.take<float>(px * C);
     int32_t *d_inst = c->io_arena.take<int32_t>(px);
     int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    HVN_CUDA(cudaMemsetAsync(d_tab, 0, tb * 8, c->stream));  // rows past n_rows go back to the caller as zeros
     int32_t *d_nr = c->io_arena.take<int32_t>(n);
     int32_t *d_offs = c->io_arena.take<int32_t>(no);
     int32_t *d_pts = c->io_arena.take<int32_t>((size_t)cap * 2 + 2);
@@ -366,6 +368,7 @@ int hvn_forward_postproc(hvn_ctx *c, const uint8_t *imgs, int B, int H, int W, f
     float *d_pred = c->io_arena.take<float>(px * oc);
     int32_t *d_inst = c->io_arena.take<int32_t>(px);
     int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    HVN_CUDA(cudaMemsetAsync(d_tab, 0, tb * 8, c->stream));  // rows past n_rows go back to the caller as zeros
     int32_t *d_nr = c->io_arena.take<int32_t>(B);
     HVN_CUDA(cudaMemcpyAsync(d_in, imgs, in_b, cudaMemcpyHostToDevice, c->stream));
     run_forward(c, d_in, B, H, W, d_pred);
@@ -432,6 +435,7 @@ int hvn_infer_tile(hvn_ctx *c, const uint8_t *img, int H, int W, int patch_in, i
     float *d_pred = c->io_arena.take<float>(px * oc);
     int32_t *d_inst = c->io_arena.take<int32_t>(px);
     int64_t *d_tab = c->io_arena.take<int64_t>(tb);
+    HVN_CUDA(cudaMemsetAsync(d_tab, 0, tb * 8, c->stream));  // rows past n_rows go back to the caller as zeros
     int32_t *d_nr = c->io_arena.take<int32_t>(1);
     int32_t *d_offs = c->io_arena.take<int32_t>(no);
     int32_t *d_pts = c->io_arena.take<int32_t>((size_t)cap * 2 + 2);

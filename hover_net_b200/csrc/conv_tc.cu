@@ -125,10 +125,11 @@ struct TcGeom {
 };
 
 constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-// XF variant: warps 10.. transform the A operand -- four (one per SM sub-partition) behind a BLOCK_N = 128 tile, eight
-// behind a BLOCK_N = 64 tile, whose K-slice leaves the tensor core in 570 instead of 800 cycles; with 576 threads the
-// register file allows 96 per thread, which the BLOCK_N = 128 epilogue does not fit in.
-template <int BLOCK_N> constexpr int xf_warps() { return BLOCK_N >= 128 ? 4 : 8; }
+// XF variant: warps 10.. transform the A operand.  The transform (~7.5 instructions per element, 500 per thread and
+// K-slice with four warps) runs about as long as the K-slice's MMAs, so its warp count sets the layer's speed: six warps
+// behind a BLOCK_N = 128 tile (512 threads: the 128 registers per thread its epilogue needs are still available), eight
+// behind a BLOCK_N = 64 tile, whose K-slice leaves the tensor core in 570 instead of 800 cycles.
+template <int BLOCK_N> constexpr int xf_warps() { return BLOCK_N >= 128 ? 6 : 8; }
 constexpr int EP_WARPS = 8;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 rows x 64 fp16
 
@@ -401,10 +402,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         const int t = threadIdx.x - (2 + EP_WARPS) * 32;
         const int l16 = t & 15, rg = t >> 4;
         const int wl = t & 31;
-        constexpr int XR = 128 / (XF_WARPS * 2);  // rows per thread
+        constexpr int RG = XF_WARPS * 2;              // row groups: rows rg, rg + RG, ...
+        constexpr int XR = (128 + RG - 1) / RG;       // rows per thread (the last one may not exist: 128 % RG)
         uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
         const uint8_t *raw_gen = smem_raw + (raw_base - smem_u32(smem_raw));
-        const int vrows = G.flat ? 128 : G.bw * G.bh;
+        const int vrows = G.flat ? 128 : G.bw * G.bh;  // rows TMA writes; the rest of a partial box keeps stale bits
         int it_global = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             float rmax = 0.f;
@@ -425,19 +427,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 const uint8_t *src = raw_gen + r * RAW_TILE_BYTES + rg * 256 + l16 * 16;
                 float4 v[XR];
 #pragma unroll
-                for (int i = 0; i < XR; ++i) v[i] = *reinterpret_cast<const float4 *>(src + i * (XF_WARPS * 2) * 256);
+                for (int i = 0; i < XR; ++i)  // rows TMA did not write read as 0: finite, and invisible to the range guard
+                    v[i] = rg + RG * i < vrows ? *reinterpret_cast<const float4 *>(src + i * RG * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                 for (int i = 0; i < XR; ++i) {
-                    const int row = rg + (XF_WARPS * 2) * i;
+                    const int row = rg + RG * i;
+                    if (128 % RG != 0 && i == XR - 1 && row >= 128) break;
                     float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
                                    fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
                     uint2 oh, ol;
-                    // range guard: running maximum over the rows TMA wrote (rows past a partial box keep stale bits),
-                    // tested once per tile -- a flag store inside this loop cost the XF layers 40-60 % (measured)
-                    const float m4 = fmaxf(fmaxf(y4[0], y4[1]), fmaxf(y4[2], y4[3]));
-                    rmax = fmaxf(rmax, row < vrows ? m4 : 0.f);
+                    // range guard: running maximum, tested once per tile (a flag store inside this loop cost the XF layers
+                    // 40-60 %, measured)
+                    rmax = fmaxf(fmaxf(rmax, fmaxf(y4[0], y4[1])), fmaxf(y4[2], y4[3]));
                     split4_f32<true>(y4, oh, ol);
                     // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
                     const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
