@@ -16,7 +16,10 @@ KEYS = [
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # raw page exported on the GPU box (tools/ncu_capture.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = []
@@ -78,7 +81,7 @@ def main(tag):
             out.append("| `%s` | %d | %.3f | %.1f %% |" % (k[:70], cnt[k], v, 100 * v / T))
         out.append("")
     for f in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
-        if not (f.startswith(tag + "_") and f.endswith(".ncu-rep")):
+        if not (f.startswith(tag + "_") and (f.endswith(".ncu-rep") or f.endswith(".raw.csv"))):
             continue
         for d in raw(os.path.join(ROOT, "gpurun_out", f)):
             out += ["## `%s` — %s" % (f, d.get("Kernel Name", ("?", ""))[0][:90]), "", "| metric | value |", "|---|---|"]
