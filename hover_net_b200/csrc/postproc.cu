@@ -822,6 +822,12 @@ k_watershed_tile(int H, int W, int big_cap, const double *__restrict__ dist_all,
 constexpr int WC_NB_BIG = 2048, WC_NB_SMALL = 256;
 constexpr unsigned short WC_NIL = 0xffffu;
 
+// One record per pixel, one 8-byte shared-memory access: fp32 priority key, link to the next pixel of its bucket list,
+// flood state (-1 outside the mask, 0 unlabelled, > 0 label).  Walking a bucket list, testing a neighbour and popping a
+// head each used to chase two or three separate arrays (kk / nxt / state); with ~30 dependent shared-memory accesses per
+// popped pixel the flood is pure latency, so halving them is what pays.
+struct __align__(8) PxRec { float key; unsigned short next; short state; };
+
 __global__ void __launch_bounds__(WT_WARPS * 32)
 k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigned char *__restrict__ fg_all,
                 const int *__restrict__ L1_all, const int *__restrict__ size1_all, const int *__restrict__ blob_root_all,
@@ -833,11 +839,9 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
     const unsigned int wmagic = (unsigned int)((0x100000000ull + (unsigned)W - 1) / (unsigned)W);
     const int m = blockIdx.x, N = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t n2 = ((size_t)N * 2 + 15) & ~(size_t)15, n4 = ((size_t)N * 4 + 15) & ~(size_t)15;
-    float *kk = reinterpret_cast<float *>(wc_smem);
-    short *state = reinterpret_cast<short *>(wc_smem + n4);
-    unsigned short *nxt = reinterpret_cast<unsigned short *>(wc_smem + n4 + n2);
-    unsigned char *qbase = wc_smem + n4 + 2 * n2;
+    const size_t n8 = ((size_t)N * 8 + 15) & ~(size_t)15;
+    PxRec *px = reinterpret_cast<PxRec *>(wc_smem);
+    unsigned char *qbase = wc_smem + n8;
     // per-warp queue storage: heads u16[NB] | bitmap u32[NB/32]
     const int NB = warp < 2 ? WC_NB_BIG : WC_NB_SMALL;
     const size_t big_bytes = WC_NB_BIG * 2 + WC_NB_BIG / 8, small_bytes = WC_NB_SMALL * 2 + WC_NB_SMALL / 8;
@@ -853,10 +857,12 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
     unsigned int lmin = 0xffffffffu, lmax = 0u;
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
         const bool f = fg[p] != 0;
-        state[p] = f ? (short)inst[p] : (short)-1;
-        const float kv = (float)dist[p] + 0.0f;  // +0.0f: -0.0 and +0.0 are equal priorities, give them one key
-        kk[p] = kv;
-        if (f) { const unsigned int ky = fkey(kv); lmin = min(lmin, ky); lmax = max(lmax, ky); }
+        PxRec r;
+        r.key = (float)dist[p] + 0.0f;  // +0.0f: -0.0 and +0.0 are equal priorities, give them one key
+        r.next = WC_NIL;
+        r.state = f ? (short)inst[p] : (short)-1;
+        px[p] = r;
+        if (f) { const unsigned int ky = fkey(r.key); lmin = min(lmin, ky); lmax = max(lmax, ky); }
     }
     for (int o = 16; o; o >>= 1) {
         lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
@@ -876,38 +882,32 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
         int b = (int)((k - kmin) * scale);
         return b < 0 ? 0 : (b >= NB ? NB - 1 : b);
     };
-    auto precedes = [&](int a, int b) {  // strict exact order of pixel a before pixel b (equal => false)
-        const float ka = kk[a], kb = kk[b];
-        if (ka != kb) return ka < kb;
-        return dist[a] < dist[b];
+    // strict exact order "pixel q (key kq) before pixel c (key kc)" (equal => false): fp32 keys, exact fp64 on a tie
+    auto precedes = [&](int q, float kq, int c, float kc) {
+        if (kq != kc) return kq < kc;
+        return dist[q] < dist[c];
     };
-    auto q_push = [&](int q) {
-        const int b = bucket_of(kk[q]);
+    // insert pixel q (key kq, its record's state already written) into its bucket list, after every entry of equal
+    // priority (push = age order)
+    auto q_push = [&](int q, float kq) {
+        const int b = bucket_of(kq);
         unsigned short cur = head[b];
         if (cur == WC_NIL) {
-            head[b] = (unsigned short)q; nxt[q] = WC_NIL;
+            head[b] = (unsigned short)q; px[q].next = WC_NIL;
             bitmap[b >> 5] |= 1u << (b & 31);
             summary |= 1ull << (b >> 5);
             return;
         }
-        if (precedes(q, cur)) { nxt[q] = cur; head[b] = (unsigned short)q; return; }
+        PxRec rc = px[cur];
+        if (precedes(q, kq, cur, rc.key)) { px[q].next = cur; head[b] = (unsigned short)q; return; }
         unsigned short prev = cur;
-        cur = nxt[cur];
-        while (cur != WC_NIL && !precedes(q, cur)) { prev = cur; cur = nxt[cur]; }
-        nxt[q] = cur; nxt[prev] = (unsigned short)q;
-    };
-    auto q_pop = [&]() {
-        const int j = __ffsll((long long)summary) - 1;
-        const unsigned int w = bitmap[j];
-        const int bit = __ffs((int)w) - 1, b = j * 32 + bit;
-        const unsigned short p = head[b], nx = nxt[p];
-        head[b] = nx;
-        if (nx == WC_NIL) {
-            const unsigned int w2 = w & ~(1u << bit);
-            bitmap[j] = w2;
-            if (!w2) summary &= ~(1ull << j);
+        cur = rc.next;
+        while (cur != WC_NIL) {
+            rc = px[cur];                               // key and link of the next entry in one access
+            if (precedes(q, kq, cur, rc.key)) break;
+            prev = cur; cur = rc.next;
         }
-        return (int)p;
+        px[q].next = cur; px[prev].next = (unsigned short)q;
     };
 
     // warps 0-1 take the large blobs first (their queues have 2048 buckets), then join the others on the small ones:
@@ -928,31 +928,52 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
             int i = base + lane;
             bool is = false;
             int p = 0;
+            float kp = 0.f;
             if (i < area) {
                 int yy = bb.x + i / bw, xx = bb.y + i % bw;
                 p = yy * W + xx;
-                is = state[p] > 0 && L1[p] == root;
+                const PxRec r = px[p];
+                is = r.state > 0 && L1[p] == root;
+                kp = r.key;
             }
             unsigned int msk = __ballot_sync(0xffffffffu, is);
             while (msk) {
                 int src = __ffs(msk) - 1;
                 msk &= msk - 1;
                 int pp = __shfl_sync(0xffffffffu, p, src);
-                if (lane == 0) q_push(pp);
+                float kk = __shfl_sync(0xffffffffu, kp, src);
+                if (lane == 0) q_push(pp, kk);
             }
         }
         if (lane == 0) {
             const long long t0 = clock64();
             int npop = 0;
             while (summary) {
-                const int idx = q_pop();
+                // pop: first non-empty bucket, its head; the head's record gives the next head and the label
+                const int j = __ffsll((long long)summary) - 1;
+                const unsigned int w = bitmap[j];
+                const int bit = __ffs((int)w) - 1, b = j * 32 + bit;
+                const int idx = head[b];
+                const PxRec e = px[idx];
+                head[b] = e.next;
+                if (e.next == WC_NIL) {
+                    const unsigned int w2 = w & ~(1u << bit);
+                    bitmap[j] = w2;
+                    if (!w2) summary &= ~(1ull << j);
+                }
                 ++npop;
                 const int y = (int)__umulhi((unsigned int)idx, wmagic), x = idx - y * W;
-                const short lab = state[idx];
+                const short lab = e.state;
                 const int q[4] = {y > 0 ? idx - W : -1, x > 0 ? idx - 1 : -1, x < W - 1 ? idx + 1 : -1, y < H - 1 ? idx + W : -1};
+                PxRec nr[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)  // up, left, right, down; label at push time
-                    if (q[j] >= 0 && state[q[j]] == 0) { state[q[j]] = lab; q_push(q[j]); }
+                for (int jn = 0; jn < 4; ++jn) {  // the four neighbour records: independent loads, in flight together
+                    nr[jn].state = -1; nr[jn].key = 0.f; nr[jn].next = WC_NIL;
+                    if (q[jn] >= 0) nr[jn] = px[q[jn]];
+                }
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn)  // up, left, right, down; label at push time
+                    if (nr[jn].state == 0) { px[q[jn]].state = lab; q_push(q[jn], nr[jn].key); }
             }
             atomicAdd(&st[m].pad[0], npop);
             atomicMax(&st[m].pad[1], (int)((clock64() - t0) >> 10));
@@ -960,7 +981,7 @@ k_watershed_cal(int H, int W, const double *__restrict__ dist_all, const unsigne
         __syncwarp();
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < N; p += blockDim.x) { short v = state[p]; inst[p] = v > 0 ? (int)v : 0; }
+    for (int p = threadIdx.x; p < N; p += blockDim.x) { short v = px[p].state; inst[p] = v > 0 ? (int)v : 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1158,7 +1179,7 @@ int postproc_run(Arena &arena, cudaStream_t stream, const float *pred, int n, in
         // patch-sized maps: per-map CTA with the flood state in shared memory; otherwise the generic kernel
         const size_t budget = 225 * 1024;
         const size_t state_bytes = (((size_t)N * 2 + 15) & ~(size_t)15), kk_bytes = (((size_t)N * 4 + 15) & ~(size_t)15);
-        const size_t cal_bytes = kk_bytes + 2 * state_bytes + 2 * (WC_NB_BIG * 2 + WC_NB_BIG / 8) +
+        const size_t cal_bytes = (((size_t)N * 8 + 15) & ~(size_t)15) + 2 * (WC_NB_BIG * 2 + WC_NB_BIG / 8) +
                                  (WT_WARPS - 2) * (WC_NB_SMALL * 2 + WC_NB_SMALL / 8);
         const size_t small_bytes = (size_t)(WT_WARPS - 1) * (WT_SMALL_CAP + 4) * 8;
         const bool use_kk = state_bytes + kk_bytes + small_bytes + (2048 + 4) * 8 <= budget;
