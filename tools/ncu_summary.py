@@ -31,8 +31,13 @@ def raw(rep):
     return res
 
 
+def _open(path):
+    import gzip
+    return gzip.open(path, "rt") if path.endswith(".gz") else open(path)
+
+
 def launches(path):
-    lines = [l for l in open(path) if not l.startswith("==")]
+    lines = [l for l in _open(path) if not l.startswith("==")]
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for row in csv.DictReader(lines):
         v = float(row["Metric Value"].replace(",", ""))
@@ -69,6 +74,8 @@ def traffic(path):
 def main(tag):
     out = ["# ncu summaries, round %s (B200, `--clock-control none`)" % tag, ""]
     lp = os.path.join(ROOT, "gpurun_out", "%s_launches.csv" % tag)
+    if not os.path.exists(lp):
+        lp += ".gz"
     if os.path.exists(lp):
         tot, cnt = launches(lp)
         T = sum(tot.values())
