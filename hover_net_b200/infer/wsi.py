@@ -135,9 +135,11 @@ class ArrayHandler(object):
         self.image_ptr = None
 
     def get_dimensions(self, read_mag=None, read_mpp=None):
-        """(x, y) at read_mag -- wsi_handler.py:49-57."""
+        """(x, y) at read_mag -- wsi_handler.py:49-57.  The reference truncates (its OpenSlide reader then resizes to that
+        size); this handler's pixels come from cv2.resize(fx, fy), whose output size ROUNDS, so the shape is rounded the
+        same way and always equals the array `read_region` serves."""
         scale = read_mag / self.metadata["base_mag"]
-        return (self.metadata["base_shape"] * scale).astype(np.int32)
+        return np.rint(self.metadata["base_shape"] * scale).astype(np.int32)
 
     def get_full_img(self, read_mag=None, read_mpp=None):
         import cv2
