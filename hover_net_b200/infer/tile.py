@@ -165,7 +165,9 @@ class InferManager(base.InferManager):
                 dist.reduce(d_pred, dst=0)
                 if rank != 0:
                     return None, None, None
-            pred_map = d_pred.cpu().numpy()
+            # whole-map post-processing + contours on the reduced map where it already lives: no 268 MB host round trip
+            pred_inst, inst_info_dict = self._post_process_on_device(ctx, d_pred, H, W)
+            return np.squeeze(d_pred.cpu().numpy()), pred_inst, inst_info_dict
         else:
             src_shape = img.shape
             padded, patch_info, _ = _prepare_patching(img, self.patch_input_shape, self.patch_output_shape, True)
@@ -173,6 +175,39 @@ class InferManager(base.InferManager):
             pred_map = _stitch(patch_info, outs, src_shape)
         pred_inst, inst_info_dict = self.post_proc_func(pred_map, nr_types=self.nr_types, return_centroids=True)
         return np.squeeze(pred_map), pred_inst, inst_info_dict
+
+    def _post_process_on_device(self, ctx, d_pred, H, W):
+        """`process` (post_proc.py:94-186) on a device-resident map [H,W,C]: hvn_postproc_dev + hvn_contours_dev, then
+        only the instance map, the table rows and the contour points come back.  Same kernels as `post_proc.process`,
+        hence the same result."""
+        import torch
+        from ..models.hovernet.post_proc import table_to_dict
+        C = int(d_pred.shape[-1])
+        max_rows, cap = max(16, H * W // 64), max(4096, H * W // 16)
+        for _attempt in range(4):  # at most: grow the table once, then the point buffer once
+            d_inst = torch.empty((H, W), dtype=torch.int32, device=d_pred.device)
+            d_tab = torch.zeros((max_rows, 10), dtype=torch.int64, device=d_pred.device)
+            d_nr = torch.zeros((1,), dtype=torch.int32, device=d_pred.device)
+            d_offs = torch.zeros((max_rows + 1,), dtype=torch.int32, device=d_pred.device)
+            d_pts = torch.empty((cap, 2), dtype=torch.int32, device=d_pred.device)
+            torch.cuda.synchronize()  # torch's stream -> the library's stream
+            ctx.postproc_dev(d_pred.data_ptr(), 1, H, W, C, self.nr_types, d_inst.data_ptr(), d_tab.data_ptr(), max_rows,
+                             d_nr.data_ptr())
+            ctx.contours_dev(d_inst.data_ptr(), d_tab.data_ptr(), d_nr.data_ptr(), 1, H, W, max_rows, d_pts.data_ptr(), cap,
+                             d_offs.data_ptr())
+            ctx.sync()
+            n = int(d_nr.item())
+            if n > max_rows:
+                max_rows = n
+                continue
+            total = int(d_offs[max_rows].item())
+            if total > cap:
+                cap = total
+                continue
+            table = d_tab[:n].cpu().numpy()
+            info = table_to_dict(table, d_offs.cpu().numpy(), d_pts[:total].cpu().numpy(), self.nr_types)
+            return d_inst.cpu().numpy(), info
+        raise RuntimeError("tile post-processing: capacity retries exhausted")
 
     def process_file_list(self, run_args):
         """Process every image tile under run_args['input_dir'] (reference infer/tile.py:150-388)."""
