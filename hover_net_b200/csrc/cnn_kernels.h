@@ -52,6 +52,7 @@ void tc_set_block_n(int n);      // tuning knobs (0 = automatic)
 void tc_set_seg_chunks(int n);
 void tc_set_res_tma(int on);
 void tc_set_res_tma_max_chunks(int n);  // largest K (in 64-channel slices) served by the RT variant
+void tc_set_xf_trunc(int on);    // XF transform warps: truncating hi/lo split (1, default) or round-to-nearest (0)
 void tc_set_halo(int mode);      // 0 off, 1 auto (where the 8 x 16 tiling fits the map), 2 every eligible layer
 
 }  // namespace hvn

@@ -122,6 +122,7 @@ struct TcGeom {
     // HALO variant: halo tile of halo_w x halo_h pixels per 64-channel block, a_plane bytes per fp16 plane
     // (1024-aligned), na slots (1 or 2)
     int halo_w, halo_h, a_plane, na;
+    int xf_trunc;  // XF transform: truncating hi/lo split (split4_relu_trunc) instead of the round-to-nearest one
 };
 
 constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
@@ -434,21 +435,36 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     v[i] = rg + RG * i < vrows ? *reinterpret_cast<const float4 *>(src + i * RG * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
+                // range guard: running maximum, tested once per tile (a flag store inside this loop cost the XF layers
+                // 40-60 %, measured).  128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7)).
+                if (G.xf_trunc) {  // truncating split (conv_epilogue.cuh): 4.5 instead of 7.25 instructions per element
 #pragma unroll
-                for (int i = 0; i < XR; ++i) {
-                    const int row = rg + RG * i;
-                    if (128 % RG != 0 && i == XR - 1 && row >= 128) break;
-                    float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
-                                   fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
-                    uint2 oh, ol;
-                    // range guard: running maximum, tested once per tile (a flag store inside this loop cost the XF layers
-                    // 40-60 %, measured)
-                    rmax = fmaxf(fmaxf(rmax, fmaxf(y4[0], y4[1])), fmaxf(y4[2], y4[3]));
-                    split4_f32<true>(y4, oh, ol);
-                    // 128B swizzle: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
-                    const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
-                    *reinterpret_cast<uint2 *>(a_hi + off) = oh;
-                    *reinterpret_cast<uint2 *>(a_lo + off) = ol;
+                    for (int i = 0; i < XR; ++i) {
+                        const int row = rg + RG * i;
+                        if (128 % RG != 0 && i == XR - 1 && row >= 128) break;
+                        const float y4[4] = {fmaf(v[i].x, sc.x, sh.x), fmaf(v[i].y, sc.y, sh.y), fmaf(v[i].z, sc.z, sh.z),
+                                             fmaf(v[i].w, sc.w, sh.w)};
+                        uint2 oh, ol;
+                        rmax = fmaxf(fmaxf(rmax, fmaxf(y4[0], y4[1])), fmaxf(y4[2], y4[3]));
+                        split4_relu_trunc(y4, oh, ol);
+                        const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
+                        *reinterpret_cast<uint2 *>(a_hi + off) = oh;
+                        *reinterpret_cast<uint2 *>(a_lo + off) = ol;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < XR; ++i) {
+                        const int row = rg + RG * i;
+                        if (128 % RG != 0 && i == XR - 1 && row >= 128) break;
+                        float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
+                                       fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
+                        uint2 oh, ol;
+                        rmax = fmaxf(fmaxf(rmax, fmaxf(y4[0], y4[1])), fmaxf(y4[2], y4[3]));
+                        split4_f32<true>(y4, oh, ol);
+                        const int off = row * 128 + ((((l16 >> 1) ^ (row & 7))) << 4) + (l16 & 1) * 8;
+                        *reinterpret_cast<uint2 *>(a_hi + off) = oh;
+                        *reinterpret_cast<uint2 *>(a_lo + off) = ol;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
@@ -870,6 +886,8 @@ static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *d
 static int g_force_block_n = 0;
 static int g_seg_chunks = 4;  // 64-channel slices per accumulation segment (4 -> 48 chained MMAs)
 static int g_res_tma = 1, g_res_tma_max_chunks = 4;  // residual tile via TMA for 1x1 layers with K <= 256 (larger K: A re-reads of N=64 tiles cost more)
+static int g_xf_trunc = 1;
+void tc_set_xf_trunc(int on) { g_xf_trunc = on; }
 static int g_halo = 1;  // 0 off, 1 auto (where the fixed 8 x 16 tiling fits the output map), 2 every eligible layer
 void tc_set_halo(int mode) { g_halo = mode; }
 void tc_set_res_tma(int on) { g_res_tma = on; }
@@ -1137,6 +1155,7 @@ void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     G.tiles_m = plan.flat ? cdiv(G.m_total, 128) : P.B * plan.tiles_x * plan.tiles_y;
     G.tiles_n = P.w.cout / plan.block_n;
     G.halo_w = plan.halo_w; G.halo_h = plan.halo_h; G.na = 0;
+    G.xf_trunc = g_xf_trunc;
     G.a_plane = (plan.halo_w * plan.halo_h * 128 + 1023) & ~1023;
     if (plan.halo) {
         bool ok = false;
