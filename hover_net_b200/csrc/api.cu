@@ -141,6 +141,11 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "tc_block_n") tc_set_block_n((int)value);
     else if (k == "tc_res_tma") tc_set_res_tma((int)value);
     else if (k == "tc_xf_trunc") tc_set_xf_trunc((int)value);
+    else if (k == "tc_ar") tc_set_ar((int)value);
+    else if (k == "tc_xf_early") tc_set_xf_early((int)value);
+    else if (k == "tc_prefetch") tc_set_prefetch((int)value);
+    else if (k == "tc_ar_min_chunks") tc_set_ar_min_chunks((int)value);
+    else if (k == "tc_ar_nres") tc_set_ar_nres((int)value);
     else if (k == "tc_res_tma_max_chunks") tc_set_res_tma_max_chunks((int)value);
     else if (k == "act_shift") {
         HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");

@@ -43,6 +43,7 @@ struct TcPlan {
     int block_n = 0;
     int flat = 0;                // 1x1 stride-1 dense view: M flattened over B*H*W
     int res_tma = 0;             // residual tile fetched by TMA (tmap_a2_hi holds its fp32 map)
+    int ar = 0, ar_gn = 1;       // A-resident variant (k_conv_ar): tmap_a2_lo = swizzled [32 px][32 ch] residual boxes; N-tiles per work unit
     int halo = 0;                // k x k stride-1 layer served from one halo tile per 64-channel block
     int halo_w = 0, halo_h = 0;  // halo extent in pixels (bw + kw - 1, bh + kh - 1)
 };
@@ -52,6 +53,11 @@ void tc_set_block_n(int n);      // tuning knobs (0 = automatic)
 void tc_set_seg_chunks(int n);
 void tc_set_res_tma(int on);
 void tc_set_res_tma_max_chunks(int n);  // largest K (in 64-channel slices) served by the RT variant
+void tc_set_ar(int on);          // 1x1 + residual, K <= 256: A-resident kernel (1, default) or the RT variant (0)
+void tc_set_ar_min_chunks(int n);  // smallest K (in 64-channel slices) served by the A-resident kernel
+void tc_set_ar_nres(int n);      // residual regions per epilogue warp (1 or 2)
+void tc_set_prefetch(int n);     // L2 prefetch distance in K-slices for flat (2-D map) operands, 0 = off
+void tc_set_xf_early(int on);    // XF: early raw-slot release + raw loads one slice ahead (1, default)
 void tc_set_xf_trunc(int on);    // XF transform warps: truncating hi/lo split (1, default) or round-to-nearest (0)
 void tc_set_halo(int mode);      // 0 off, 1 auto (where the 8 x 16 tiling fits the map), 2 every eligible layer
 

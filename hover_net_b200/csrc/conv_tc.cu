@@ -79,6 +79,11 @@ __device__ __forceinline__ void tma_4d(uint32_t dst, const void *tmap, uint32_t 
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// L2 prefetch of a tensor-map box: no shared memory, no barrier -- used to run several K-slices ahead of the loads on
+// operands that come from HBM (the rings below hold 2-3 slices, less than one DRAM round trip under load)
+__device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -122,9 +127,12 @@ struct TcGeom {
     // HALO variant: halo tile of halo_w x halo_h pixels per 64-channel block, a_plane bytes per fp16 plane
     // (1024-aligned), na slots (1 or 2)
     int halo_w, halo_h, a_plane, na;
+    int pf;        // flat (2-D map) operands: L2 prefetch distance in K-slices (0 = off)
+    int xf_early;  // XF: raw slot released right after its values are in registers, raw loads one slice ahead of the W wait
     int xf_trunc;  // XF transform: truncating hi/lo split (split4_relu_trunc) instead of the round-to-nearest one
 };
 
+constexpr int SMEM_LIMIT = 232448;       // opt-in dynamic shared memory per CTA (227 KB)
 constexpr int TC_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 // XF variant: warps 10.. transform the A operand.  The transform (~7.5 instructions per element, 500 per thread and
 // K-slice with four warps) runs about as long as the K-slice's MMAs, so its warp count sets the layer's speed: six warps
@@ -238,6 +246,47 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
           } else {
             int it_global = 0;
             int tile_count = 0;
+            // L2 prefetch cursor, G.pf K-slices ahead of the loads through the same (tile, slice) sequence.  Flat layers
+            // only: their A operand is a whole encoder tensor streamed from HBM (571 MB for d1's running sum at 16
+            // patches); with a 2-slot raw ring the XF layers ran at one DRAM round trip per two K-slices.
+            const bool pf_on = G.flat && G.pf > 0;
+            int pf_tile = blockIdx.x, pf_it = 0;
+            auto pf_step = [&]() {
+                if (pf_tile >= total_tiles) return;
+                const int m0p = (pf_tile / G.tiles_n) * 128;
+                if constexpr (XF) tma_prefetch_2d(&tm_a_hi, pf_it * 64, m0p);
+                else if (G.k1 > 0 && pf_it >= G.k1) {
+                    tma_prefetch_2d(&tm_a2_hi, (pf_it - G.k1) * 64, m0p);
+                    tma_prefetch_2d(&tm_a2_lo, (pf_it - G.k1) * 64, m0p);
+                } else {
+                    tma_prefetch_2d(&tm_a_hi, pf_it * 64, m0p);
+                    tma_prefetch_2d(&tm_a_lo, pf_it * 64, m0p);
+                }
+                if (++pf_it == kiters) { pf_it = 0; pf_tile += gridDim.x; }
+            };
+            if (pf_on) for (int i = 0; i < G.pf; ++i) pf_step();
+            // XF, G.xf_early: the raw fp32 tile of K-slice i+1 is requested BEFORE this thread blocks on the operand stage of
+            // slice i (whose release needs the MMAs of slice i-2) -- its own cursor through the (tile, slice) sequence.
+            // Together with the transform warps handing the raw slot back as soon as its values are in registers, a raw
+            // slot cycles in (load latency + LDS) instead of (load latency + stage wait + transform).
+            int rw_tile = blockIdx.x, rw_it = 0, rw_count = 0;
+            auto raw_step = [&]() {
+                if (rw_tile >= total_tiles) return;
+                const int tmr = rw_tile / G.tiles_n;
+                const int r = rw_count & 1;
+                mbar_wait(rempty_bar(r), (((uint32_t)(rw_count >> 1)) & 1u) ^ 1u);
+                mbar_expect_tx(rfull_bar(r), (uint32_t)((G.flat ? 128 : G.bw * G.bh) * 256));
+                if (G.flat) tma_2d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), rw_it * 64, tmr * 128);
+                else {
+                    const int per_img = G.tiles_x * G.tiles_y;
+                    const int ni = tmr / per_img, rr = tmr - ni * per_img;
+                    tma_4d(raw_base + r * RAW_TILE_BYTES, &tm_a_hi, rfull_bar(r), rw_it * 64, (rr - (rr / G.tiles_x) * G.tiles_x) * G.bw,
+                           (rr / G.tiles_x) * G.bh, ni);
+                }
+                ++rw_count;
+                if (++rw_it == kiters) { rw_it = 0; rw_tile += gridDim.x; }
+            };
+            if (XF && G.xf_early) raw_step();
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int tm = tile / G.tiles_n, tn = tile - tm * G.tiles_n;
                 int n_img = 0, y0 = 0, x0 = 0;
@@ -257,9 +306,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     mbar_expect_tx(rfull_bar(r), RAW_TILE_BYTES);
                     tma_2d(raw_base + r * RAW_TILE_BYTES, &tm_a2_hi, rfull_bar(r), tn * BLOCK_N, (int)m0);
                     ++tile_count;
+                    if (G.pf > 0) {  // residual of the tile after next -> L2 (the ring itself holds one tile of look-ahead)
+                        const int t2 = tile + 2 * (int)gridDim.x;
+                        if (t2 < total_tiles) tma_prefetch_2d(&tm_a2_hi, (t2 % G.tiles_n) * BLOCK_N, (t2 / G.tiles_n) * 128);
+                    }
                 }
                 for (int it = 0; it < kiters; ++it, ++it_global) {
-                    if constexpr (XF) {
+                    if (pf_on) pf_step();
+                    if (XF && G.xf_early) raw_step();   // slice it_global + 1
+                    else if constexpr (XF) {
                         // raw fp32 A tile of this K-slice -> staging ring (tm_a_hi is the fp32 map).  Issued BEFORE the
                         // wait for the operand stage: the raw slot frees up a whole transform earlier than the stage does,
                         // and a raw load that waits for the stage costs the XF layers 15 % (measured, r2d vs r2a)
@@ -433,6 +488,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 #pragma unroll
                 for (int i = 0; i < XR; ++i)  // rows TMA did not write read as 0: finite, and invisible to the range guard
                     v[i] = rg + RG * i < vrows ? *reinterpret_cast<const float4 *>(src + i * RG * 256) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // y = x*scale + shift in place: in-order issue puts every instruction below behind the completed LDS of
+                // this lane, so the raw slot can go back to the producer NOW (G.xf_early) -- a whole stage wait + split +
+                // store phase before the old hand-back at the end of the slice
+#pragma unroll
+                for (int i = 0; i < XR; ++i)
+                    v[i] = make_float4(fmaf(v[i].x, sc.x, sh.x), fmaf(v[i].y, sc.y, sh.y), fmaf(v[i].z, sc.z, sh.z), fmaf(v[i].w, sc.w, sh.w));
+                if (G.xf_early) {
+                    __syncwarp();
+                    if (wl == 0) mbar_arrive(rempty_bar(r));
+                }
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 uint8_t *a_hi = smem_gen + s * STAGE_BYTES, *a_lo = a_hi + A_TILE_BYTES;
                 // range guard: running maximum, tested once per tile (a flag store inside this loop cost the XF layers
@@ -442,8 +507,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     for (int i = 0; i < XR; ++i) {
                         const int row = rg + RG * i;
                         if (128 % RG != 0 && i == XR - 1 && row >= 128) break;
-                        const float y4[4] = {fmaf(v[i].x, sc.x, sh.x), fmaf(v[i].y, sc.y, sh.y), fmaf(v[i].z, sc.z, sh.z),
-                                             fmaf(v[i].w, sc.w, sh.w)};
+                        const float y4[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
                         uint2 oh, ol;
                         rmax = fmaxf(fmaxf(rmax, fmaxf(y4[0], y4[1])), fmaxf(y4[2], y4[3]));
                         split4_relu_trunc(y4, oh, ol);
@@ -456,8 +520,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     for (int i = 0; i < XR; ++i) {
                         const int row = rg + RG * i;
                         if (128 % RG != 0 && i == XR - 1 && row >= 128) break;
-                        float y4[4] = {fmaxf(v[i].x * sc.x + sh.x, 0.f), fmaxf(v[i].y * sc.y + sh.y, 0.f),
-                                       fmaxf(v[i].z * sc.z + sh.z, 0.f), fmaxf(v[i].w * sc.w + sh.w, 0.f)};
+                        float y4[4] = {fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f), fmaxf(v[i].z, 0.f), fmaxf(v[i].w, 0.f)};
                         uint2 oh, ol;
                         rmax = fmaxf(fmaxf(rmax, fmaxf(y4[0], y4[1])), fmaxf(y4[2], y4[3]));
                         split4_f32<true>(y4, oh, ol);
@@ -468,7 +531,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (wl == 0) { mbar_arrive(full_bar(s)); mbar_arrive(rempty_bar(r)); }
+                if (wl == 0) { mbar_arrive(full_bar(s)); if (!G.xf_early) mbar_arrive(rempty_bar(r)); }
             }
             if (rmax > 65504.f && P.a.flag) *P.a.flag = 1u;
         }
@@ -616,6 +679,231 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 ++tcount_e;
             }
         }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AR variant: 1x1 stride-1 convolution + residual with a RESIDENT A operand (the conv3 of the encoder's residual units,
+// reference net_utils.py:233-266; K <= 256, cout = 4K).
+// The RT variant above walks (M-tile, N-tile) pairs and fetches A (128 px x K, hi and lo) and W (64 cout x K) again for
+// each of them: 24 B of L2->SM traffic per output element at K = 256 against the ~11 TB/s the SMs can take while the
+// tensor core runs, i.e. a 190 TFLOP/s cap (measured 167-172).  Here a CTA owns a work unit = one M-tile x `gn`
+// consecutive N-tiles: the A tile is fetched ONCE per unit and stays in shared memory while the unit's W tiles stream
+// through a ring, which leaves 1 (A) + 8 (W) + 4 (residual) B per output element.
+//  * A slices have their own full / empty barriers: the MMA warp releases slice kc right after the unit's LAST tile has
+//    issued its MMAs on it, so the next unit's slice 0 is in flight three slices before the unit ends (no bubble).
+//  * The fp32 residual never meets the epilogue's staging tile: every epilogue warp owns a [32 px][32 ch] fp32 region
+//    (4 KB, 128 B rows, SWIZZLE_128B) that TMA fills with the residual of the warp's own quadrant / column half; the warp
+//    adds its accumulator rows IN PLACE (lane = pixel: conflict-free 16 B accesses thanks to the swizzle), reads the
+//    region back transposed (8 lanes = the 32 channels of one pixel = 128 B coalesced stores) and then requests the
+//    next tile's residual box itself -- no cross-warp hand-off, no separate transpose buffer.
+struct ArGeom {
+    int tiles_m, tiles_n, kchunks, gn, ngroups, wst;
+    int pf;    // L2 prefetch of the next unit's A slices and of residual boxes two tiles ahead (0 = off)
+    int nres;  // residual regions per epilogue warp: 2 where shared memory allows (K <= 128), so that two tiles' residual
+               // boxes are in flight -- the layers this serves sit close to the HBM roofline, bytes in flight are what count
+    long long m_total;
+};
+constexpr int AR_BN = 64;
+constexpr int AR_A_SLICE = 2 * A_TILE_BYTES;          // hi | lo of one 64-channel slice
+constexpr int AR_W_STAGE = 2 * AR_BN * 128;           // [w_hi | w_lo] of one (64-channel, 64-cout) tile
+constexpr int AR_MAX_K = 4, AR_MAX_WST = 8;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_ar(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+          const __grid_constant__ CUtensorMap tm_res, const ConvParams P, const ArGeom G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = smem_base + (uint32_t)G.kchunks * AR_A_SLICE;
+    const uint32_t r_base = w_base + (uint32_t)G.wst * AR_W_STAGE;       // nres x 8 x 4 KB residual / write-out regions
+    const uint32_t bar_base = r_base + (uint32_t)G.nres * EP_WARPS * 4096u;
+    auto afull_bar = [&](int k) { return bar_base + 8u * k; };
+    auto aempty_bar = [&](int k) { return bar_base + 8u * (AR_MAX_K + k); };
+    auto wfull_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + s); };
+    auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + AR_MAX_WST + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 2 + s); };
+    auto rfull_bar = [&](int w, int r) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + 2 * w + r); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + 2 * EP_WARPS);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 4 * AR_BN;  // two buffers of [hi*hi + lo*hi | hi*lo]
+
+    if (warp == 0 && lane == 0) {
+        for (int k = 0; k < AR_MAX_K; ++k) { mbar_init(afull_bar(k), 1); mbar_init(aempty_bar(k), 1); }
+        for (int s = 0; s < AR_MAX_WST; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EP_WARPS * 32); }
+        for (int w = 0; w < EP_WARPS; ++w) { mbar_init(rfull_bar(w, 0), 1); mbar_init(rfull_bar(w, 1), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int units = G.tiles_m * G.ngroups;
+
+    if (warp == 0) {
+        // ===================== TMA producer: A slices once per unit, W tiles per (N-tile, slice) =====================
+        if (lane == 0) {
+            int uc = 0, wit = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+                const int tm = u / G.ngroups, ng = u - tm * G.ngroups;
+                const int m0 = tm * 128;
+                if (G.pf > 0 && u + (int)gridDim.x < units) {  // the next unit's A tile -> L2, a whole unit ahead
+                    const int m0n = ((u + (int)gridDim.x) / G.ngroups) * 128;
+                    if (m0n != m0)
+                        for (int kc = 0; kc < G.kchunks; ++kc) { tma_prefetch_2d(&tm_a_hi, kc * 64, m0n); tma_prefetch_2d(&tm_a_lo, kc * 64, m0n); }
+                }
+                for (int j = 0; j < G.gn; ++j) {
+                    const int tn = ng * G.gn + j;
+                    for (int kc = 0; kc < G.kchunks; ++kc, ++wit) {
+                        if (j == 0) {
+                            mbar_wait(aempty_bar(kc), ((uint32_t)uc & 1u) ^ 1u);
+                            mbar_expect_tx(afull_bar(kc), (uint32_t)AR_A_SLICE);
+                            const uint32_t a = smem_base + (uint32_t)kc * AR_A_SLICE;
+                            tma_2d(a, &tm_a_hi, afull_bar(kc), kc * 64, m0);
+                            tma_2d(a + A_TILE_BYTES, &tm_a_lo, afull_bar(kc), kc * 64, m0);
+                        }
+                        const int s = wit % G.wst;
+                        mbar_wait(wempty_bar(s), (((uint32_t)(wit / G.wst)) & 1u) ^ 1u);
+                        mbar_expect_tx(wfull_bar(s), (uint32_t)AR_W_STAGE);
+                        const uint32_t b = w_base + (uint32_t)s * AR_W_STAGE;
+                        tma_3d(b, &tm_w_hi, wfull_bar(s), kc * 64, tn * AR_BN, 0);
+                        tma_3d(b + AR_BN * 128, &tm_w_lo, wfull_bar(s), kc * 64, tn * AR_BN, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(AR_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * AR_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int uc = 0, wit = 0, tc = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++uc) {
+                for (int j = 0; j < G.gn; ++j, ++tc) {
+                    const int as = tc & 1;
+                    mbar_wait(tempty_bar(as), (((uint32_t)(tc >> 1)) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * AR_BN);
+                    for (int kc = 0; kc < G.kchunks; ++kc, ++wit) {
+                        if (j == 0) mbar_wait(afull_bar(kc), (uint32_t)uc & 1u);
+                        const int s = wit % G.wst;
+                        mbar_wait(wfull_bar(s), ((uint32_t)(wit / G.wst)) & 1u);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)kc * AR_A_SLICE;
+                        const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
+                                       db_hi = umma_desc(w_base + (uint32_t)s * AR_W_STAGE);  // [w_hi | w_lo]: 128 contiguous rows
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc2, (kc > 0 || k > 0) ? 1u : 0u);
+                            tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
+                        }
+                        tc_commit(wempty_bar(s));
+                        if (j == G.gn - 1) tc_commit(aempty_bar(kc));  // the unit's last use of this A slice
+                    }
+                    tc_commit(tfull_bar(as));
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2, widx = warp - 2;
+        const uint32_t reg_addr0 = r_base + (uint32_t)(widx * G.nres) * 4096u;
+        const int sub_px = lane >> 3, sub_g = lane & 7;
+        // lane 0 only: this warp's residual box of the CTA's tl-th tile (units in round-robin order, gn tiles per unit)
+        auto box_of = [&](int tl, int &c0, int &c1) {
+            const int u = blockIdx.x + (tl / G.gn) * (int)gridDim.x;
+            if (u >= units) return false;
+            const int tm = u / G.ngroups;
+            c0 = ((u - tm * G.ngroups) * G.gn + tl % G.gn) * AR_BN + half * 32;
+            c1 = tm * 128 + quad * 32;
+            return true;
+        };
+        auto request_res = [&](int tl) {
+            int c0, c1;
+            if (!box_of(tl, c0, c1)) return;
+            const int r = tl % G.nres;
+            mbar_expect_tx(rfull_bar(widx, r), 4096u);
+            tma_2d(reg_addr0 + (uint32_t)r * 4096u, &tm_res, rfull_bar(widx, r), c0, c1);
+            if (G.pf > 0 && box_of(tl + 2, c0, c1)) tma_prefetch_2d(&tm_res, c0, c1);  // two tiles further on: HBM -> L2
+        };
+        if (lane == 0) for (int r = 0; r < G.nres; ++r) request_res(r);
+        int tc = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int tm = u / G.ngroups, ng = u - tm * G.ngroups;
+            const long long mrow0 = (long long)tm * 128 + quad * 32;
+            for (int j = 0; j < G.gn; ++j, ++tc) {
+                const int tn = ng * G.gn + j;
+                const int ch4 = tn * AR_BN + half * 32 + sub_g * 4;   // this lane's 4 channels in the write-out mapping
+                float4 esc = make_float4(1.f, 1.f, 1.f, 1.f), esh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.scale && P.out_split.hi) {
+                    esc = *reinterpret_cast<const float4 *>(P.scale + ch4);
+                    esh = *reinterpret_cast<const float4 *>(P.shift + ch4);
+                }
+                const int as = tc & 1;
+                mbar_wait(tfull_bar(as), ((uint32_t)(tc >> 1)) & 1u);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * AR_BN + half * 32);
+                uint32_t r0[32], r1[32];
+                tc_ld32(t_addr, r0);                      // a_hi*w_hi + a_lo*w_hi
+                tc_ld32(t_addr + (uint32_t)AR_BN, r1);    // a_hi*w_lo
+                tc_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty_bar(as));
+                const int rr = tc % G.nres;
+                uint8_t *reg = smem_raw + (reg_addr0 + (uint32_t)rr * 4096u - smem_u32(smem_raw));
+                mbar_wait(rfull_bar(widx, rr), ((uint32_t)(tc / G.nres)) & 1u);
+                // in place: region[pixel = lane][channel] = acc * 2^-e + residual   (2^-e exact, so fma == mul then add)
+                const float *osc = P.w.oscale + tn * AR_BN + half * 32;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 ws = __ldg(reinterpret_cast<const float4 *>(osc + 4 * c));
+                    float4 *p = reinterpret_cast<float4 *>(reg + lane * 128 + ((c ^ (lane & 7)) << 4));
+                    float4 v = *p;
+                    v.x = fmaf(__uint_as_float(r0[4 * c]) + __uint_as_float(r1[4 * c]), ws.x, v.x);
+                    v.y = fmaf(__uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]), ws.y, v.y);
+                    v.z = fmaf(__uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]), ws.z, v.z);
+                    v.w = fmaf(__uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]), ws.w, v.w);
+                    *p = v;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int px = it * 4 + sub_px;
+                    const float4 t = *reinterpret_cast<const float4 *>(reg + px * 128 + ((sub_g ^ (px & 7)) << 4));
+                    const long long m = mrow0 + px;
+                    if (m < G.m_total) {
+                        if (P.out_raw.p) *reinterpret_cast<float4 *>(P.out_raw.p + m * P.out_raw.sW + ch4) = t;
+                        if (P.out_split.hi) {
+                            float v[4] = {t.x, t.y, t.z, t.w};
+                            if (P.scale) { v[0] = v[0] * esc.x + esh.x; v[1] = v[1] * esc.y + esh.y; v[2] = v[2] * esc.z + esh.z; v[3] = v[3] * esc.w + esh.w; }
+                            if (P.relu) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+                            }
+                            store_split4(P.out_split, m * P.out_split.sW + ch4, v);
+                        }
+                    }
+                }
+                // the region is free: request the next tile's residual (generic accesses above -> async-proxy write below)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) request_res(tc + G.nres);
+            }
         }
     }
     tc_fence_before();
@@ -870,13 +1158,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
-                   const cuuint32_t *box, const cuuint32_t *estr, bool raw_f32 = false) {
+                   const cuuint32_t *box, const cuuint32_t *estr, bool raw_f32 = false, bool swz_f32 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     alignas(64) CUtensorMap tm;
     CUresult r = fn(&tm, raw_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base,
                     dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    raw_f32 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    (raw_f32 && !swz_f32) ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     memcpy(dst, &tm, sizeof(tm));
@@ -886,6 +1174,17 @@ static bool encode(unsigned char *dst, void *base, int rank, const cuuint64_t *d
 static int g_force_block_n = 0;
 static int g_seg_chunks = 4;  // 64-channel slices per accumulation segment (4 -> 48 chained MMAs)
 static int g_res_tma = 1, g_res_tma_max_chunks = 4;  // residual tile via TMA for 1x1 layers with K <= 256 (larger K: A re-reads of N=64 tiles cost more)
+// 1x1 + residual layers: A-resident variant (k_conv_ar) instead of RT where K >= g_ar_min_chunks 64-channel slices
+// (0 = never).  Measured on B200 (gpurun_out/r3a_layers_orig16_{base,aronly}.log): d2 (K = 256) 0.194 -> 0.173 ms; d0 / d1
+// (K = 64 / 128) stream 8 B of fp32 residual per output element for 2K FLOPs and sit at the HBM roofline either way.
+static int g_ar = 1, g_ar_min_chunks = 1, g_ar_nres = 2;
+void tc_set_ar(int on) { g_ar = on; }
+void tc_set_ar_min_chunks(int n) { g_ar_min_chunks = n; }
+void tc_set_ar_nres(int n) { g_ar_nres = n; }
+static int g_pf = 4;        // L2 prefetch distance (K-slices) for flat operands; 0 = off
+void tc_set_prefetch(int n) { g_pf = n < 0 ? 0 : n; }
+static int g_xf_early = 1;
+void tc_set_xf_early(int on) { g_xf_early = on; }
 static int g_xf_trunc = 1;
 void tc_set_xf_trunc(int on) { g_xf_trunc = on; }
 static int g_halo = 1;  // 0 off, 1 auto (where the fixed 8 x 16 tiling fits the output map), 2 every eligible layer
@@ -930,7 +1229,7 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
     }
     if (xf && bn != 128 && bn != 64) return false;
     cuuint32_t ones[4] = {1, 1, 1, 1};
-    plan.res_tma = 0;
+    plan.res_tma = 0; plan.ar = 0; plan.ar_gn = 1;
     if (P.res.p && !P.up2 && !two && !xf && plan.flat && g_res_tma && w.cout % 64 == 0 && w.cin_pad / 64 <= g_res_tma_max_chunks) {
         const RawRef &r = P.res;
         const bool dense_r = (long long)r.sW * r.w == r.sH && (long long)r.sH * r.h == r.sN && r.h == P.ho && r.w == P.wo;
@@ -939,6 +1238,35 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
             cuuint64_t rstr[1] = {(cuuint64_t)r.sW * 4};
             cuuint32_t rbox[2] = {64, 128};
             if (encode(plan.tmap_a2_hi, r.p, 2, rdims, rstr, rbox, ones, true)) { plan.res_tma = 1; bn = 64; plan.block_n = 64; }
+            // AR (resident A operand): flat pixel-major addressing of the outputs, residual boxes of [32 px][32 ch] fp32
+            // with the 128 B swizzle (tmap_a2_lo, free in this mode)
+            auto dense_out = [&](long long sW, long long sH, long long sN, int h, int wd) {
+                return sW * wd == sH && sH * h == sN && h == P.ho && wd == P.wo && sW % 4 == 0;
+            };
+            const bool raw_ok = !P.out_raw.p || (dense_out(P.out_raw.sW, P.out_raw.sH, P.out_raw.sN, P.out_raw.h, P.out_raw.w) &&
+                                                 !(reinterpret_cast<uintptr_t>(P.out_raw.p) & 15));
+            const bool split_ok = !P.out_split.hi || (dense_out(P.out_split.sW, P.out_split.sH, P.out_split.sN, P.out_split.h, P.out_split.w) &&
+                                                      !(reinterpret_cast<uintptr_t>(P.out_split.hi) & 7) && !(reinterpret_cast<uintptr_t>(P.out_split.lo) & 7));
+            cuuint32_t abox[2] = {32, 32};
+            if (plan.res_tma && raw_ok && split_ok && w.cin_pad / 64 <= AR_MAX_K && (long long)P.B * r.h * r.w < (1ll << 31) - 256 &&
+                encode(plan.tmap_a2_lo, r.p, 2, rdims, rstr, abox, ones, true, true)) {
+                // work units = M-tiles x groups of gn N-tiles; gn = the divisor of tiles_n with the smallest estimated
+                // time on the SMs: waves x (gn tiles + the exposed part of the A fetch)
+                int sms = 148;
+                { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+                const int kch = w.cin_pad / 64, tn = w.cout / 64;
+                const long long tmn = cdiv((long long)P.B * P.ho * P.wo, 128);
+                const double t_tile = std::max(kch * 572.0, (kch * 16384.0 + 32768.0) / 45.0), t_a = kch * 32768.0 / 45.0 * 0.5;
+                double best = 1e30; int best_gn = 1;
+                for (int gn = 1; gn <= tn; ++gn) {
+                    if (tn % gn) continue;
+                    const long long units = tmn * (tn / gn);
+                    const double t = (double)cdiv(units, sms) * (gn * t_tile + t_a);
+                    if (t < best * 0.999) { best = t; best_gn = gn; }
+                    else if (t <= best * 1.001) best_gn = gn;   // ties: the larger group re-reads A less often
+                }
+                plan.ar = 1; plan.ar_gn = best_gn;
+            }
         }
     }
     plan.halo = 0;
@@ -1057,7 +1385,6 @@ static void launch_tm(const ConvParams &P, const TcPlan &plan, const TcGeom &G, 
     k_conv_tc<BLOCK_N, STAGES, MODE, XF, RT><<<grid, TC_THREADS + (XF ? xf_warps<BLOCK_N>() * 32 : 0), smem, s>>>(a_hi, a_lo, w_hi, w_lo, a2_hi, a2_lo, P, G);
 }
 
-constexpr int SMEM_LIMIT = 232448;
 template <int BLOCK_N, int STAGES> constexpr int halo_fixed_smem() {
     return STAGES * 2 * BLOCK_N * 128 + 8 * (2 * STAGES + 4) + 48 + EP_WARPS * 32 * 32 * 4 + 1024 + 1024;
 }
@@ -1145,7 +1472,41 @@ void launch_conv0_tc(const uint8_t *img, int B, int H, int W, int pad, const Con
     k_conv0_tc<<<std::min(tiles, sms), C0T_THREADS, C0T_SMEM, s>>>(w_hi, w_lo, img, B, H, W, pad, w.oscale, scale, shift, out);
 }
 
+static void launch_ar(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
+    ArGeom G;
+    G.kchunks = P.w.cin_pad / 64;
+    G.m_total = (long long)P.B * P.ho * P.wo;
+    G.tiles_m = cdiv(G.m_total, 128);
+    G.tiles_n = P.w.cout / AR_BN;
+    G.gn = plan.ar_gn; G.ngroups = G.tiles_n / G.gn;
+    G.pf = g_pf;
+    int fixed = 1024 + G.kchunks * AR_A_SLICE + EP_WARPS * 4096 + 8 * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + 2 * EP_WARPS) + 16;
+    G.nres = (g_ar_nres >= 2 && fixed + EP_WARPS * 4096 + 4 * AR_W_STAGE <= SMEM_LIMIT) ? 2 : 1;
+    fixed += (G.nres - 1) * EP_WARPS * 4096;
+    G.wst = std::min(AR_MAX_WST, (SMEM_LIMIT - fixed) / AR_W_STAGE);
+    HVN_CHECK(G.wst >= 2, -1, "conv_ar: weight ring does not fit shared memory");
+    const int smem = fixed + G.wst * AR_W_STAGE;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = std::min(G.tiles_m * G.ngroups, sms);
+    CUtensorMap a_hi, a_lo, w_hi, w_lo, res;
+    memcpy(&a_hi, plan.tmap_a_hi, 128); memcpy(&a_lo, plan.tmap_a_lo, 128);
+    memcpy(&w_hi, plan.tmap_w_hi, 128); memcpy(&w_lo, plan.tmap_w_lo, 128);
+    memcpy(&res, plan.tmap_a2_lo, 128);
+    k_conv_ar<<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, res, P, G);
+}
+
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
+    if (plan.ar && g_ar && P.w.cin_pad / 64 >= g_ar_min_chunks) { launch_ar(P, plan, s); return; }  // else: the RT variant
     TcGeom G;
     G.flat = plan.flat; G.bw = plan.bw; G.bh = plan.bh; G.tiles_x = plan.tiles_x; G.tiles_y = plan.tiles_y;
     G.kchunks = P.w.cin_pad / 64;
@@ -1156,6 +1517,8 @@ void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     G.tiles_n = P.w.cout / plan.block_n;
     G.halo_w = plan.halo_w; G.halo_h = plan.halo_h; G.na = 0;
     G.xf_trunc = g_xf_trunc;
+    G.xf_early = g_xf_early;
+    G.pf = g_pf;
     G.a_plane = (plan.halo_w * plan.halo_h * 128 + 1023) & ~1023;
     if (plan.halo) {
         bool ok = false;

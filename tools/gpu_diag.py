@@ -190,3 +190,54 @@ def sweep():
 
 if __name__ == "__main__" and "sweep" in sys.argv[1:]:
     sweep()
+
+
+def ab(mode="original", B=16, configs=("base:",), reps=5):
+    """A/B per-layer device times inside ONE process: the configurations (launch-time knobs, "tag:key=value,...") are
+    interleaved `reps` times and the per-layer MEDIAN is reported, so that clock / thermal drift between separate runs
+    (measured: up to 10 % on layers no knob touches) cancels."""
+    import re
+    from hover_net_b200.models.hovernet.net_desc import create_model
+    nt = {"fast": 6, "original": 5}[mode]
+    x = synth.make_patches(B, arch.PATCH_GEOMETRY[mode][0], seed=7)
+    net = create_model(mode=mode, nr_types=nt)
+    net.load_state_dict(synth.make_state_dict(mode, nt, 0))
+    net.ctx.set_option("chunk", B)
+    net.ctx.set_option("branch_streams", 0)
+    cfgs = []
+    for c in configs:
+        tag, _, opts = c.partition(":")
+        cfgs.append((tag, [(kv.split("=")[0], int(kv.split("=")[1])) for kv in opts.split(",") if "=" in kv]))
+    keys = sorted({k for _, o in cfgs for k, _ in o})
+    defaults = {"tc_xf_early": 1, "tc_prefetch": 4, "tc_ar": 1, "tc_ar_min_chunks": 1, "tc_ar_nres": 2, "tc_xf_trunc": 1, "tc_res_tma": 1}
+    net.ctx.forward(x)
+    net.ctx.set_option("profile", 3)
+    times = {t: {} for t, _ in cfgs}
+    order = []
+    for rep in range(reps):
+        for tag, opts in cfgs:
+            for k in keys: net.ctx.set_option(k, defaults[k])
+            for k, v in opts: net.ctx.set_option(k, v)
+            net.ctx.forward(x)
+            seen = {}
+            for l in net.ctx.debug_log().split("\n"):
+                m = re.match(r"(\S+)\s+(conv_tc|conv_ref|conv0|bnrelu|head)\s.*?([\d.]+) ms", l)
+                if not m: continue
+                n = m.group(1); seen[n] = seen.get(n, 0) + 1
+                if seen[n] > 1: n += "'" * (seen[n] - 1)
+                if rep == 0 and tag == cfgs[0][0]: order.append(n)
+                times[tag].setdefault(n, []).append(float(m.group(3)))
+    med = {t: {n: float(np.median(v)) for n, v in d.items()} for t, d in times.items()}
+    t0 = cfgs[0][0]
+    print("%-46s" % ("layer (%s B=%d, median of %d)" % (mode, B, reps)) + "".join("%11s" % t for t, _ in cfgs))
+    for n in order:
+        vals = [med[t].get(n, float("nan")) for t, _ in cfgs]
+        if any(abs(v - vals[0]) > 0.02 * vals[0] for v in vals[1:]):
+            print("%-46s" % n[:46] + "".join("%11.4f" % v for v in vals))
+    print("%-46s" % "TOTAL" + "".join("%11.3f" % sum(med[t].values()) for t, _ in cfgs))
+    net.ctx.close()
+
+
+if __name__ == "__main__" and "ab" in sys.argv[1:]:
+    i = sys.argv.index("ab")
+    ab(sys.argv[i + 1], int(sys.argv[i + 2]), sys.argv[i + 3:], reps=int(os.environ.get("AB_REPS", "5")))
