@@ -146,6 +146,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "tc_prefetch") tc_set_prefetch((int)value);
     else if (k == "tc_ar_min_chunks") tc_set_ar_min_chunks((int)value);
     else if (k == "tc_ar_nres") tc_set_ar_nres((int)value);
+    else if (k == "tc_ar_min_wst") tc_set_ar_min_wst((int)value);
     else if (k == "tc_res_tma_max_chunks") tc_set_res_tma_max_chunks((int)value);
     else if (k == "act_shift") {
         HVN_CHECK(c->model, HVN_ERR_STATE, "context has no model");

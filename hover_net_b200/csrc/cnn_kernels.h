@@ -55,7 +55,8 @@ void tc_set_res_tma(int on);
 void tc_set_res_tma_max_chunks(int n);  // largest K (in 64-channel slices) served by the RT variant
 void tc_set_ar(int on);          // 1x1 + residual, K <= 256: A-resident kernel (1, default) or the RT variant (0)
 void tc_set_ar_min_chunks(int n);  // smallest K (in 64-channel slices) served by the A-resident kernel
-void tc_set_ar_nres(int n);      // residual regions per epilogue warp (1 or 2)
+void tc_set_ar_nres(int n);      // residual regions per epilogue warp: upper limit (1..4)
+void tc_set_ar_min_wst(int n);   // ... while the weight ring keeps at least this many stages
 void tc_set_prefetch(int n);     // L2 prefetch distance in K-slices for flat (2-D map) operands, 0 = off
 void tc_set_xf_early(int on);    // XF: early raw-slot release + raw loads one slice ahead (1, default)
 void tc_set_xf_trunc(int on);    // XF transform warps: truncating hi/lo split (1, default) or round-to-nearest (0)

@@ -707,14 +707,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 struct ArGeom {
     int tiles_m, tiles_n, kchunks, gn, ngroups, wst;
     int pf;    // L2 prefetch of the next unit's A slices and of residual boxes two tiles ahead (0 = off)
-    int nres;  // residual regions per epilogue warp: 2 where shared memory allows (K <= 128), so that two tiles' residual
-               // boxes are in flight -- the layers this serves sit close to the HBM roofline, bytes in flight are what count
+    int nres;  // residual regions per epilogue warp (1..4, as shared memory allows): that many tiles' residual boxes are in
+               // flight -- the layers this serves sit close to the HBM roofline, bytes in flight are what count
     long long m_total;
 };
 constexpr int AR_BN = 64;
 constexpr int AR_A_SLICE = 2 * A_TILE_BYTES;          // hi | lo of one 64-channel slice
 constexpr int AR_W_STAGE = 2 * AR_BN * 128;           // [w_hi | w_lo] of one (64-channel, 64-cout) tile
-constexpr int AR_MAX_K = 4, AR_MAX_WST = 8;
+constexpr int AR_MAX_K = 4, AR_MAX_WST = 8, AR_MAX_NRES = 4;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_ar(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -731,8 +731,8 @@ k_conv_ar(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
     auto wempty_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + AR_MAX_WST + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 2 + s); };
-    auto rfull_bar = [&](int w, int r) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + 2 * w + r); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + 2 * EP_WARPS);
+    auto rfull_bar = [&](int w, int r) { return bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + AR_MAX_NRES * w + r); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + AR_MAX_NRES * EP_WARPS);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 4 * AR_BN;  // two buffers of [hi*hi + lo*hi | hi*lo]
@@ -741,7 +741,8 @@ k_conv_ar(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
         for (int k = 0; k < AR_MAX_K; ++k) { mbar_init(afull_bar(k), 1); mbar_init(aempty_bar(k), 1); }
         for (int s = 0; s < AR_MAX_WST; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EP_WARPS * 32); }
-        for (int w = 0; w < EP_WARPS; ++w) { mbar_init(rfull_bar(w, 0), 1); mbar_init(rfull_bar(w, 1), 1); }
+        for (int w = 0; w < EP_WARPS; ++w)
+            for (int r = 0; r < AR_MAX_NRES; ++r) mbar_init(rfull_bar(w, r), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1177,7 +1178,10 @@ static int g_res_tma = 1, g_res_tma_max_chunks = 4;  // residual tile via TMA fo
 // 1x1 + residual layers: A-resident variant (k_conv_ar) instead of RT where K >= g_ar_min_chunks 64-channel slices
 // (0 = never).  Measured on B200 (gpurun_out/r3a_layers_orig16_{base,aronly}.log): d2 (K = 256) 0.194 -> 0.173 ms; d0 / d1
 // (K = 64 / 128) stream 8 B of fp32 residual per output element for 2K FLOPs and sit at the HBM roofline either way.
-static int g_ar = 1, g_ar_min_chunks = 1, g_ar_nres = 2;
+// Region sets: 2 beat 1 on K <= 128; 3-4 sets are SLOWER (they shorten the weight ring to 4 stages: d0 0.484 -> 0.531 ms,
+// d1 0.270 -> 0.287), and a 2-stage weight ring costs d2 19 % (gpurun_out/r3f_ab_*.log).
+static int g_ar = 1, g_ar_min_chunks = 1, g_ar_nres = 2, g_ar_min_wst = 3;
+void tc_set_ar_min_wst(int n) { g_ar_min_wst = n < 2 ? 2 : n; }
 void tc_set_ar(int on) { g_ar = on; }
 void tc_set_ar_min_chunks(int n) { g_ar_min_chunks = n; }
 void tc_set_ar_nres(int n) { g_ar_nres = n; }
@@ -1480,8 +1484,11 @@ static void launch_ar(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     G.tiles_n = P.w.cout / AR_BN;
     G.gn = plan.ar_gn; G.ngroups = G.tiles_n / G.gn;
     G.pf = g_pf;
-    int fixed = 1024 + G.kchunks * AR_A_SLICE + EP_WARPS * 4096 + 8 * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + 2 * EP_WARPS) + 16;
-    G.nres = (g_ar_nres >= 2 && fixed + EP_WARPS * 4096 + 4 * AR_W_STAGE <= SMEM_LIMIT) ? 2 : 1;
+    int fixed = 1024 + G.kchunks * AR_A_SLICE + EP_WARPS * 4096 + 8 * (2 * AR_MAX_K + 2 * AR_MAX_WST + 4 + AR_MAX_NRES * EP_WARPS) + 16;
+    // residual region sets: as many as fit beside a weight ring of g_ar_min_wst stages (bytes in flight on the fp32 residual
+    // stream are what these HBM-bound layers need), at most g_ar_nres
+    G.nres = 1;
+    while (G.nres < std::min(g_ar_nres, AR_MAX_NRES) && fixed + G.nres * EP_WARPS * 4096 + g_ar_min_wst * AR_W_STAGE <= SMEM_LIMIT) ++G.nres;
     fixed += (G.nres - 1) * EP_WARPS * 4096;
     G.wst = std::min(AR_MAX_WST, (SMEM_LIMIT - fixed) / AR_W_STAGE);
     HVN_CHECK(G.wst >= 2, -1, "conv_ar: weight ring does not fit shared memory");
