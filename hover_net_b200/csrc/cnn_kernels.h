@@ -43,6 +43,8 @@ struct TcPlan {
     int block_n = 0;
     int flat = 0;                // 1x1 stride-1 dense view: M flattened over B*H*W
     int res_tma = 0;             // residual tile fetched by TMA (tmap_a2_hi holds its fp32 map)
+    int rs = 0, rs_bw = 0, rs_bh = 0;   // row-stacked variant (k_conv_rs): A maps in tmap_a2_hi / lo, stacked weight maps below
+    unsigned char tmap_rs_w_hi[128], tmap_rs_w_lo[128];
     int ar = 0, ar_gn = 1;       // A-resident variant (k_conv_ar): tmap_a2_lo = swizzled [32 px][32 ch] residual boxes; N-tiles per work unit
     int halo = 0;                // k x k stride-1 layer served from one halo tile per 64-channel block
     int halo_w = 0, halo_h = 0;  // halo extent in pixels (bw + kw - 1, bh + kh - 1)
@@ -58,6 +60,7 @@ void tc_set_ar_min_chunks(int n);  // smallest K (in 64-channel slices) served b
 void tc_set_ar_nres(int n);      // residual regions per epilogue warp: upper limit (1..4)
 void tc_set_ar_min_wst(int n);   // ... while the weight ring keeps at least this many stages
 void tc_set_prefetch(int n);     // L2 prefetch distance in K-slices for flat (2-D map) operands, 0 = off
+void tc_set_rowstack(int on);    // grouped k x k layers on k_conv_rs (1, default) or the per-tap / HALO path (0)
 void tc_set_xf_early(int on);    // XF: early raw-slot release + raw loads one slice ahead (1, default)
 void tc_set_xf_trunc(int on);    // XF transform warps: truncating hi/lo split (1, default) or round-to-nearest (0)
 void tc_set_halo(int mode);      // 0 off, 1 auto (where the 8 x 16 tiling fits the map), 2 every eligible layer

@@ -916,6 +916,197 @@ k_conv_ar(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------
+// RS variant ("row-stacked"): the decoder's grouped k x k convolutions (128 -> 32 channels in 4 groups, valid padding,
+// reference net_utils.py:101-118: DenseBlock conv2), stored block-diagonal dense.
+// A tcgen05 SS-mode instruction costs max(71.6, N/2) cycles whatever N is (tools/umma_rate_probe.cu): with N = 32 couts
+// the per-tap path issues kh*kw*8*2 = 400 (5x5) instructions of 71.6 cycles per 128 pixels -- 28 TFLOP/s, a tenth of the
+// kernel's time for 1 % of its FLOPs.  Here the kw taps of a filter ROW are stacked along N instead:
+//     D[(y, xi), (kx, c)] = sum_{ky, cin} in[y + ky, xi, cin] * w[ky, kx, cin, c]          N = kw * 32 (160 / 96)
+// for every INPUT column xi of the tile's rows, and the epilogue folds the columns (col2im along x):
+//     out[y, x, c] = sum_kx D[(y, x + kx), (kx, c)].
+// The weight tensor [tap = ky*kw + kx][cout][cin] already IS [ky][(kx, cout)][cin], so a second tensor map over the same
+// memory serves the stacked tiles.  Per K-step: a_hi*w_hi, a_hi*w_lo, a_lo*w_hi as three N = kw*32 instructions into ONE
+// accumulator (3 x 80 cycles at N = 160): 40 K-steps = 9 600 cycles per tile instead of 28 600.
+// M-tile = bh full input rows (bw = input width, bw * bh <= 128); accumulation segments as in k_conv_tc.
+// Epilogue: warps (quad, half) own accumulator rows quad*32.. and channels half*16.. of every kx; they drop their rows
+// into a per-half staging tile (row stride kw*16 + 4 floats: 16-byte accesses by 8 consecutive rows hit 8 different bank
+// groups), meet at a named barrier, and each thread then sums its own pixel's kw shifted rows and stores 64 B of fp32.
+struct RsGeom {
+    int bw, bh, rows, tiles_y, tiles_m, kchunks, kh, seg;
+};
+template <int KW> constexpr int rs_stages() { return KW >= 5 ? 2 : 3; }
+template <int KW> constexpr int rs_max_rows() { return KW >= 5 ? 124 : 128; }   // staging rows that fit beside the operand ring
+template <int KW> constexpr int rs_stage_bytes() { return 2 * A_TILE_BYTES + 2 * KW * 32 * 128; }
+template <int KW> constexpr int rs_smem() {
+    return 1024 + rs_stages<KW>() * rs_stage_bytes<KW>() + 2 * rs_max_rows<KW>() * (KW * 16 + 4) * 4 + 8 * (2 * rs_stages<KW>() + 4) + 16;
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+template <int KW>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_rs(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+          const ConvParams P, const RsGeom G) {
+    constexpr int N = KW * 32, STAGES = rs_stages<KW>(), STAGE_BYTES = rs_stage_bytes<KW>();
+    constexpr int W_PLANE = N * 128;                 // one fp16 plane of the stacked weight tile
+    constexpr int NH = KW * 16, STRIDE = NH + 4;     // accumulators per thread; staging row stride in floats
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t st_base = smem_base + STAGES * STAGE_BYTES;                        // 2 halves x [rows][STRIDE] fp32
+    const uint32_t bar_base = st_base + 2u * rs_max_rows<KW>() * STRIDE * 4u;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 512;              // two accumulation buffers of N <= 160 columns at 0 and 256
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EP_WARPS * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const int kiters = G.kh * G.kchunks;             // K-slices per tile: (filter row, 64-channel slice)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(2 * G.rows * 128 + 2 * W_PLANE);
+            int itg = 0;
+            for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+                const int n_img = tile / G.tiles_y, y0 = (tile - n_img * G.tiles_y) * G.bh;
+                for (int ky = 0; ky < G.kh; ++ky)
+                    for (int kc = 0; kc < G.kchunks; ++kc, ++itg) {
+                        const int s = itg % STAGES;
+                        mbar_wait(empty_bar(s), (((uint32_t)(itg / STAGES)) & 1u) ^ 1u);
+                        mbar_expect_tx(full_bar(s), tx);
+                        const uint32_t sa = smem_base + (uint32_t)s * STAGE_BYTES;
+                        tma_4d(sa, &tm_a_hi, full_bar(s), kc * 64, 0, y0 + ky, n_img);                 // bh full input rows, shifted by ky
+                        tma_4d(sa + A_TILE_BYTES, &tm_a_lo, full_bar(s), kc * 64, 0, y0 + ky, n_img);
+                        tma_3d(sa + 2 * A_TILE_BYTES, &tm_w_hi, full_bar(s), kc * 64, 0, ky);           // all kx taps of filter row ky
+                        tma_3d(sa + 2 * A_TILE_BYTES + W_PLANE, &tm_w_lo, full_bar(s), kc * 64, 0, ky);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int itg = 0, scount = 0;
+            for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+                for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
+                    const int as = scount & 1;
+                    mbar_wait(tempty_bar(as), (((uint32_t)(scount >> 1)) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+                    const int it1 = min(it0 + G.seg, kiters);
+                    for (int it = it0; it < it1; ++it, ++itg) {
+                        const int s = itg % STAGES;
+                        mbar_wait(full_bar(s), ((uint32_t)(itg / STAGES)) & 1u);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)s * STAGE_BYTES;
+                        const uint64_t da_hi = umma_desc(sa), da_lo = umma_desc(sa + A_TILE_BYTES),
+                                       db_hi = umma_desc(sa + 2 * A_TILE_BYTES), db_lo = umma_desc(sa + 2 * A_TILE_BYTES + W_PLANE);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_hi + ko, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                            tc_mma_f16(d_tmem, da_hi + ko, db_lo + ko, idesc, 1u);
+                            tc_mma_f16(d_tmem, da_lo + ko, db_hi + ko, idesc, 1u);
+                        }
+                        tc_commit(empty_bar(s));
+                    }
+                    tc_commit(tfull_bar(as));
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9): drain segments, fold the kx columns, store =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int row = quad * 32 + lane;               // accumulator row = (input row py, input column px) of the tile
+        float *stage = reinterpret_cast<float *>(smem_raw + (st_base - smem_u32(smem_raw))) + half * rs_max_rows<KW>() * STRIDE;
+        const int py = row / G.bw, px = row - py * G.bw;
+        const float *osc = P.w.oscale + half * 16;
+        int scount = 0;
+        for (int tile = blockIdx.x; tile < G.tiles_m; tile += gridDim.x) {
+            const int n_img = tile / G.tiles_y, y0 = (tile - n_img * G.tiles_y) * G.bh;
+            float acc[NH];
+#pragma unroll
+            for (int j = 0; j < NH; ++j) acc[j] = 0.f;
+            for (int it0 = 0; it0 < kiters; it0 += G.seg, ++scount) {
+                const int as = scount & 1;
+                mbar_wait(tfull_bar(as), ((uint32_t)(scount >> 1)) & 1u);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + half * 16);
+#pragma unroll
+                for (int kx = 0; kx < KW; ++kx) {
+                    uint32_t r[16];
+                    tc_ld16(t_addr + (uint32_t)(kx * 32), r);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[kx * 16 + j] += __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(as));
+            }
+            // rows >= G.rows of the MMA tile were never written by TMA (stale shared memory): they stay out of the staging tile
+            if (row < G.rows) {
+                float4 *dst = reinterpret_cast<float4 *>(stage + row * STRIDE);
+#pragma unroll
+                for (int q = 0; q < NH / 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+            const int oy = y0 + py;
+            if (row < G.rows && px < P.wo && oy < P.ho) {   // px + kx < bw: the kw rows read below belong to the same input row
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = 0.f;
+#pragma unroll
+                for (int kx = 0; kx < KW; ++kx) {
+                    const float4 *src = reinterpret_cast<const float4 *>(stage + (row + kx) * STRIDE + kx * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 t = src[q];
+                        o[4 * q] += t.x; o[4 * q + 1] += t.y; o[4 * q + 2] += t.z; o[4 * q + 3] += t.w;
+                    }
+                }
+                float *out = P.out_raw.p + n_img * P.out_raw.sN + (long long)oy * P.out_raw.sH + (long long)px * P.out_raw.sW + half * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 ws = __ldg(reinterpret_cast<const float4 *>(osc + 4 * q));
+                    *reinterpret_cast<float4 *>(out + 4 * q) = make_float4(o[4 * q] * ws.x, o[4 * q + 1] * ws.y, o[4 * q + 2] * ws.z, o[4 * q + 3] * ws.w);
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // staging tile free for the next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stem on the tensor core: conv0 7x7x3 -> 64 on the uint8 image (reference net_desc.py:27-35,103,115), BN+ReLU,
 // split store.  GEMM view: M = output pixels, N = 64, K = 7 rows x 24 (21 bytes of one image row = 7 taps x 3 channels,
 // padded to 24) = 168, padded to 192 = three 64-wide K-slices; the 8th "row" and the 3 pad bytes carry zero weights.
@@ -1187,6 +1378,8 @@ void tc_set_ar_min_chunks(int n) { g_ar_min_chunks = n; }
 void tc_set_ar_nres(int n) { g_ar_nres = n; }
 static int g_pf = 4;        // L2 prefetch distance (K-slices) for flat operands; 0 = off
 void tc_set_prefetch(int n) { g_pf = n < 0 ? 0 : n; }
+static int g_rs = 1;   // grouped k x k decoder layers: row-stacked kernel (k_conv_rs) instead of the per-tap / HALO path
+void tc_set_rowstack(int on) { g_rs = on; }
 static int g_xf_early = 1;
 void tc_set_xf_early(int on) { g_xf_early = on; }
 static int g_xf_trunc = 1;
@@ -1270,6 +1463,27 @@ bool tc_plan(const ConvParams &P, TcPlan &plan) {
                     else if (t <= best * 1.001) best_gn = gn;   // ties: the larger group re-reads A less often
                 }
                 plan.ar = 1; plan.ar_gn = best_gn;
+            }
+        }
+    }
+    // RS (row-stacked) variant for the decoder's grouped k x k layers: second A map (full input rows) in tmap_a2_hi / lo,
+    // stacked weight maps over the same [tap][cout][cin] memory read as [ky][(kx, cout)][cin]
+    plan.rs = 0;
+    if (w.taps > 1 && w.kh == w.kw && (w.kw == 3 || w.kw == 5) && P.stride == 1 && P.pad_t == 0 && w.cout == 32 && w.cin_pad == 128 &&
+        !xf && !two && !P.up2 && !P.res.p && P.out_raw.p && !P.out_split.hi && P.a.w == P.wo + w.kw - 1 && P.a.h == P.ho + w.kh - 1 &&
+        !(reinterpret_cast<uintptr_t>(P.out_raw.p) & 15) && P.out_raw.sW % 4 == 0 && P.out_raw.sH % 4 == 0 && P.out_raw.sN % 4 == 0) {
+        const int max_rows = w.kw == 5 ? rs_max_rows<5>() : rs_max_rows<3>();
+        if (P.a.w <= max_rows) {
+            const int bw = P.a.w, bh = std::max(1, std::min(max_rows / bw, P.ho));
+            cuuint64_t dims[4] = {(cuuint64_t)P.a.c, (cuuint64_t)P.a.w, (cuuint64_t)P.a.h, (cuuint64_t)P.B};
+            cuuint64_t str[3] = {(cuuint64_t)P.a.sW * 2, (cuuint64_t)P.a.sH * 2, (cuuint64_t)P.a.sN * 2};
+            cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+            cuuint64_t wdims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)(w.kw * w.cout), (cuuint64_t)w.kh};
+            cuuint64_t wstr[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout * w.kw * 2};
+            cuuint32_t wbox[3] = {64, (cuuint32_t)(w.kw * w.cout), 1};
+            if (encode(plan.tmap_a2_hi, P.a.hi, 4, dims, str, box, ones) && encode(plan.tmap_a2_lo, P.a.lo, 4, dims, str, box, ones) &&
+                encode(plan.tmap_rs_w_hi, w.hi, 3, wdims, wstr, wbox, ones) && encode(plan.tmap_rs_w_lo, w.lo, 3, wdims, wstr, wbox, ones)) {
+                plan.rs = 1; plan.rs_bw = bw; plan.rs_bh = bh;
             }
         }
     }
@@ -1512,7 +1726,36 @@ static void launch_ar(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     k_conv_ar<<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, res, P, G);
 }
 
+template <int KW>
+static void launch_rs(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
+    RsGeom G;
+    G.bw = plan.rs_bw; G.bh = plan.rs_bh; G.rows = G.bw * G.bh;
+    G.tiles_y = cdiv(P.ho, G.bh); G.tiles_m = P.B * G.tiles_y;
+    G.kchunks = P.w.cin_pad / 64; G.kh = P.w.kh; G.seg = g_seg_chunks;
+    constexpr int smem = rs_smem<KW>();
+    static_assert(smem <= SMEM_LIMIT, "conv_rs: shared memory budget exceeded");
+    static bool attr = false;
+    if (!attr) {
+        HVN_CUDA(cudaFuncSetAttribute(k_conv_rs<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    memcpy(&a_hi, plan.tmap_a2_hi, 128); memcpy(&a_lo, plan.tmap_a2_lo, 128);
+    memcpy(&w_hi, plan.tmap_rs_w_hi, 128); memcpy(&w_lo, plan.tmap_rs_w_lo, 128);
+    k_conv_rs<KW><<<std::min(G.tiles_m, sms), TC_THREADS, smem, s>>>(a_hi, a_lo, w_hi, w_lo, P, G);
+}
+
 void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
+    if (plan.rs && g_rs) {
+        if (P.w.kw == 5) launch_rs<5>(P, plan, s); else launch_rs<3>(P, plan, s);
+        return;
+    }
     if (plan.ar && g_ar && P.w.cin_pad / 64 >= g_ar_min_chunks) { launch_ar(P, plan, s); return; }  // else: the RT variant
     TcGeom G;
     G.flat = plan.flat; G.bw = plan.bw; G.bh = plan.bh; G.tiles_x = plan.tiles_x; G.tiles_y = plan.tiles_y;

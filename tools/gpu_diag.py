@@ -99,7 +99,7 @@ def tc(mode="fast", nt=6, verbose=False):
 
 
 if __name__ == "__main__" and "tc" in sys.argv[1:]:
-    tc(*(sys.argv[sys.argv.index("tc") + 1:sys.argv.index("tc") + 2] or ["fast"]))
+    tc(*(sys.argv[sys.argv.index("tc") + 1:sys.argv.index("tc") + 2] or ["fast"]), verbose="v" in sys.argv)
 
 
 def layers(mode="fast", B=8):
@@ -209,7 +209,7 @@ def ab(mode="original", B=16, configs=("base:",), reps=5):
         tag, _, opts = c.partition(":")
         cfgs.append((tag, [(kv.split("=")[0], int(kv.split("=")[1])) for kv in opts.split(",") if "=" in kv]))
     keys = sorted({k for _, o in cfgs for k, _ in o})
-    defaults = {"tc_xf_early": 1, "tc_prefetch": 4, "tc_ar": 1, "tc_ar_min_chunks": 1, "tc_ar_nres": 2, "tc_ar_min_wst": 3, "tc_xf_trunc": 1, "tc_res_tma": 1}
+    defaults = {"tc_rowstack": 1, "tc_xf_early": 1, "tc_prefetch": 4, "tc_ar": 1, "tc_ar_min_chunks": 1, "tc_ar_nres": 2, "tc_ar_min_wst": 3, "tc_xf_trunc": 1, "tc_res_tma": 1}
     net.ctx.forward(x)
     net.ctx.set_option("profile", 3)
     times = {t: {} for t, _ in cfgs}
