@@ -109,7 +109,10 @@ def measured_traffic(kernel_class, mode):
             t = json.load(open(path))
             if t.get("mode", "fast") != mode:
                 continue
-            k = t["kernels"].get("k_conv_tc" if kernel_class == "conv_tc" else "k_conv_ref")
+            # the tcgen05 convolution class = k_conv_tc + its A-resident (k_conv_ar) and row-stacked (k_conv_rs) variants
+            names = ("k_conv_tc", "k_conv_ar", "k_conv_rs") if kernel_class == "conv_tc" else ("k_conv_ref",)
+            ks = [t["kernels"][n] for n in names if n in t["kernels"]]
+            k = {"dram_bytes": sum(x["dram_bytes"] for x in ks), "launches": sum(x["launches"] for x in ks)}
             return {"dram_bytes_per_launch": k["dram_bytes"] / k["launches"], "launches": k["launches"],
                     "batch": t["batch"], "source": "profiles/" + os.path.basename(path) + " (" + t["command"] + ")"}
     except Exception:
@@ -502,7 +505,7 @@ def run_ours(args):
                          "avg_launch_ms": d["ms"] / max(1, d["launches"]), "launches_per_step": d["launches"],
                          "traffic": measured_traffic(dom, mode),
                          "note": "algorithmic 2*MACs of the reference graph; every product is formed three times in "
-                                 "fp16 (hi*hi+hi*lo+lo*hi, issued as two MMA instructions per K-step), so frac <= 1/3 "
+                                 "fp16 (hi*hi+hi*lo+lo*hi, issued as two or three MMA instructions per K-step), so frac <= 1/3 "
                                  "by construction"},
             "roofline_postproc": {"bound": "hbm", "unit": "GB/s", "peak": hbm, "peak_source": pk_kind + " hbm_gbs",
                                   "algorithmic_bytes_per_step": pp_bytes,

@@ -33,6 +33,10 @@
 //   shared-memory address bits (tools/umma_shift_probe.cu, measured on B200: any 128 B-row start offset and
 //   any SBO multiple of 128 B reads what TMA wrote), so no re-layout is needed.  Weights stream through their
 //   own ring, one (tap, 64-channel) tile per stage.
+// * Two specialised sibling kernels further down: k_conv_ar (1x1 + fp32 residual with the A tile resident in shared
+//   memory while the unit's weight tiles stream; residual added in place in swizzled per-warp regions) and k_conv_rs
+//   (the decoder's grouped k x k layers: the kw taps of a filter row stacked along N, col2im in the epilogue).
+// * Flat (2-D map) operands streamed from HBM get a cp.async.bulk.prefetch.tensor L2 cursor a few K-slices ahead.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
