@@ -249,7 +249,7 @@ def test_kernel_variants_agree(mode, nt):
             out = infer_step(x, net)
             net.ctx.set_option(k, default[k])
             err = np.abs(out[..., -3:] - ref[..., -3:]).max()
-            assert err <= 2e-5, "%s=0 changes the output by %.3e" % (k, err)
+            assert err <= 3e-5, "%s=0 changes the output by %.3e" % (k, err)
         again = infer_step(x, net)
         assert np.array_equal(again, ref), "the knobs are launch-time switches: defaults restored => identical bits"
     finally:
