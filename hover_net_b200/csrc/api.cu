@@ -142,6 +142,7 @@ int hvn_set_option(hvn_ctx *c, const char *key, int64_t value) {
     else if (k == "tc_res_tma") tc_set_res_tma((int)value);
     else if (k == "tc_xf_trunc") tc_set_xf_trunc((int)value);
     else if (k == "tc_ar") tc_set_ar((int)value);
+    else if (k == "tc_lean_epi") tc_set_lean_epi((int)value);
     else if (k == "tc_rowstack") tc_set_rowstack((int)value);
     else if (k == "tc_xf_early") tc_set_xf_early((int)value);
     else if (k == "tc_prefetch") tc_set_prefetch((int)value);

@@ -61,6 +61,7 @@ void tc_set_ar_nres(int n);      // residual regions per epilogue warp: upper li
 void tc_set_ar_min_wst(int n);   // ... while the weight ring keeps at least this many stages
 void tc_set_prefetch(int n);     // L2 prefetch distance in K-slices for flat (2-D map) operands, 0 = off
 void tc_set_rowstack(int on);    // grouped k x k layers on k_conv_rs (1, default) or the per-tap / HALO path (0)
+void tc_set_lean_epi(int on);    // k_conv_tc write-out with per-tile precomputed output offsets (1, default)
 void tc_set_xf_early(int on);    // XF: early raw-slot release + raw loads one slice ahead (1, default)
 void tc_set_xf_trunc(int on);    // XF transform warps: truncating hi/lo split (1, default) or round-to-nearest (0)
 void tc_set_halo(int mode);      // 0 off, 1 auto (where the 8 x 16 tiling fits the map), 2 every eligible layer

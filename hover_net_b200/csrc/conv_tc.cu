@@ -132,6 +132,7 @@ struct TcGeom {
     // (1024-aligned), na slots (1 or 2)
     int halo_w, halo_h, a_plane, na;
     int pf;        // flat (2-D map) operands: L2 prefetch distance in K-slices (0 = off)
+    int lean_epi;  // write-out with per-tile precomputed output offsets (plain / residual epilogues)
     int xf_early;  // XF: raw slot released right after its values are in registers, raw loads one slice ahead of the W wait
     int xf_trunc;  // XF transform: truncating hi/lo split (split4_relu_trunc) instead of the round-to-nearest one
 };
@@ -596,6 +597,16 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                     }
                 }
             }
+            // Element offsets of this lane's pixel in the two outputs (-1 = no such output / no such pixel), computed ONCE per
+            // tile and shuffled to the write-out mapping below.  The write-out used to rebuild n*sN + oy*sH + ox*sW in
+            // 64-bit arithmetic for every (pixel, 32-channel block) behind four shuffles: half of its 1 878 instructions per
+            // 128 x 128 tile (SASS), and that loop paces every split-output layer with few K-slices (decoder conv1 layers:
+            // 12 k cycles per tile against 1 600 of MMA).
+            long long off_s = -1, off_r = -1;
+            if (MODE != EPI_UP2 && valid) {
+                if (P.out_split.hi) off_s = n_img * P.out_split.sN + (long long)oy * P.out_split.sH + (long long)ox * P.out_split.sW;
+                if (P.out_raw.p) off_r = n_img * P.out_raw.sN + (long long)oy * P.out_raw.sH + (long long)ox * P.out_raw.sW;
+            }
             // BN scale / shift of this lane's 4 channels per 32-channel block: requested before the accumulator wait
             float4 esc[NCH], esh[NCH], ews[NCH];
 #pragma unroll
@@ -651,6 +662,34 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ C
                 __syncwarp();
                 const int ch = tn * BLOCK_N + cb + c0 + sub_g * 4;
                 constexpr int PB = MODE == EPI_UP2 ? (XF ? 2 : 4) : 8;  // pixels-per-lane whose loads are in flight together
+                if (MODE != EPI_UP2 && G.lean_epi) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int src = it * 4 + sub_px;
+                        const long long so = __shfl_sync(0xffffffffu, off_s, src), ro = __shfl_sync(0xffffffffu, off_r, src);
+                        const float4 t = *reinterpret_cast<const float4 *>(&ep_tile[src * 32 + ((sub_g ^ (src & 7)) << 2)]);
+                        const float4 ws = ews[c0 / 32];
+                        float v[4] = {t.x * ws.x, t.y * ws.y, t.z * ws.z, t.w * ws.w};
+                        if constexpr (MODE == EPI_RES) {
+                            float4 r;
+                            if constexpr (RT) r = *reinterpret_cast<const float4 *>(res_tile + (quad * 32 + src) * BLOCK_N + cb + c0 + sub_g * 4);
+                            else r = rpre[c0 / 32][it];
+                            v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+                        }
+                        if (ro >= 0) *reinterpret_cast<float4 *>(P.out_raw.p + ro + ch) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (so >= 0) {
+                            if (P.scale) {
+                                const float4 sc = esc[c0 / 32], sh = esh[c0 / 32];
+                                v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y; v[2] = v[2] * sc.z + sh.z; v[3] = v[3] * sc.w + sh.w;
+                            }
+                            if (P.relu) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+                            }
+                            store_split4(P.out_split, so + ch, v);
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int bt = 0; bt < 8 / PB; ++bt) {
                     int pv[PB], pn[PB], py[PB], px[PB];
@@ -1384,6 +1423,8 @@ static int g_pf = 4;        // L2 prefetch distance (K-slices) for flat operands
 void tc_set_prefetch(int n) { g_pf = n < 0 ? 0 : n; }
 static int g_rs = 1;   // grouped k x k decoder layers: row-stacked kernel (k_conv_rs) instead of the per-tap / HALO path
 void tc_set_rowstack(int on) { g_rs = on; }
+static int g_lean_epi = 1;
+void tc_set_lean_epi(int on) { g_lean_epi = on; }
 static int g_xf_early = 1;
 void tc_set_xf_early(int on) { g_xf_early = on; }
 static int g_xf_trunc = 1;
@@ -1772,6 +1813,7 @@ void tc_launch(const ConvParams &P, const TcPlan &plan, cudaStream_t s) {
     G.halo_w = plan.halo_w; G.halo_h = plan.halo_h; G.na = 0;
     G.xf_trunc = g_xf_trunc;
     G.xf_early = g_xf_early;
+    G.lean_epi = g_lean_epi;
     G.pf = g_pf;
     G.a_plane = (plan.halo_w * plan.halo_h * 128 + 1023) & ~1023;
     if (plan.halo) {

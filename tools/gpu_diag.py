@@ -209,7 +209,7 @@ def ab(mode="original", B=16, configs=("base:",), reps=5):
         tag, _, opts = c.partition(":")
         cfgs.append((tag, [(kv.split("=")[0], int(kv.split("=")[1])) for kv in opts.split(",") if "=" in kv]))
     keys = sorted({k for _, o in cfgs for k, _ in o})
-    defaults = {"tc_rowstack": 1, "tc_xf_early": 1, "tc_prefetch": 4, "tc_ar": 1, "tc_ar_min_chunks": 1, "tc_ar_nres": 2, "tc_ar_min_wst": 3, "tc_xf_trunc": 1, "tc_res_tma": 1}
+    defaults = {"tc_lean_epi": 1, "tc_rowstack": 1, "tc_xf_early": 1, "tc_prefetch": 4, "tc_ar": 1, "tc_ar_min_chunks": 1, "tc_ar_nres": 2, "tc_ar_min_wst": 3, "tc_xf_trunc": 1, "tc_res_tma": 1}
     net.ctx.forward(x)
     net.ctx.set_option("profile", 3)
     times = {t: {} for t, _ in cfgs}
