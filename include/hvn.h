@@ -78,7 +78,14 @@ int hvn_finalize_weights(hvn_ctx *ctx);
  *                      tuning knobs (defaults are the measured best): "tc_halo" = 0 | 1 | 2 (k x k layers read
  *                      shifted windows of one halo tile: off / where its 8x16 tiling fits / every eligible layer),
  *                      "tc_seg_chunks" (64-channel slices per accumulation segment), "tc_block_n", "tc_res_tma",
- *                      "xform", "fuse_shortcut", "fuse_up2", "branch_streams", "flood_impl". */
+ *                      "tc_rowstack" = 0 | 1 (grouped k x k layers on the row-stacked kernel k_conv_rs),
+ *                      "tc_ar" = 0 | 1, "tc_ar_min_chunks", "tc_ar_nres", "tc_ar_min_wst" (1x1 + residual layers on the
+ *                      A-resident kernel k_conv_ar: smallest K in 64-channel slices, residual region sets per warp, minimum
+ *                      weight-ring depth), "tc_prefetch" (L2 prefetch distance in K-slices for flat operands, 0 = off),
+ *                      "tc_xf_trunc", "tc_xf_early", "tc_lean_epi" (XF producer / write-out variants; 0 = the older path),
+ *                      "xform", "fuse_shortcut", "fuse_up2", "branch_streams", "flood_impl".
+ *                      The tc_* knobs are process-wide launch-time switches; every setting gives the same results to
+ *                      fp32-accumulation noise (tests/test_cnn_gpu.py::test_kernel_variants_agree). */
 int hvn_set_option(hvn_ctx *ctx, const char *key, int64_t value);
 const char *hvn_debug_log(const hvn_ctx *ctx);
 /* counters: "kernel_launches", "tc_launches", "pp_launches" (post-processing and contour kernels), "last_flops" (algorithmic 2*MACs of the
